@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Benchmark of the FCN deploy hot path (BASELINE.json metric: SA FCN 192x208 slices/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode bf16|fp32] [--subjects S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the CPU restatement of the reference loop
+
+One step = one pass of the hot path (percentile rescale + pad + build_FCN forward +
+argmax/crop) over a batch of S synthetic short-axis subjects (192x208x10x50 = 500 slices
+each) per GPU.  `value` times the device-resident path (inputs already in HBM);
+`e2e.value` times the public host-buffer call (pinned host -> H2D -> compute -> D2H of the
+label volumes) over the same batch.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SA = (192, 208, 10, 50)
+FLOP_PER_SLICE = 3.13737216e9          # algorithmic FLOPs, SA 192x208, 4 classes
+POOL = 8                               # distinct synthetic subjects cycled through a batch
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_sample(frames: int, threads: int):
+    """The reference's loop (deploy_network.py:89-116) restated on CPU: global percentile
+    rescale, then ONE forward per time frame with batch Z=10, float32 (PyTorch/oneDNN stands in
+    for TensorFlow-CPU, which is not installable here).  Bounded sample: `frames` frames of one
+    synthetic SA subject.  Returns (slices_per_s, seconds, n_slices)."""
+    import torch
+    from oracle import deploy_oracle as do
+    from ukbb_cardiac_b200 import synth
+    torch.set_num_threads(threads)
+    w = synth.make_weights(0, 4)
+    vol = synth.make_stack(0, (SA[0], SA[1], SA[2], frames))
+    run = do.make_runner(w)
+    run(np.zeros((1, 32, 32, 1), np.float32))            # warm oneDNN primitives
+    t0 = time.perf_counter()
+    pred, _ = do.deploy_sequence(vol, run)
+    dt = time.perf_counter() - t0
+    n = SA[2] * frames
+    return n / dt, dt, n
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    frames = args.ref_frames
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_sample(1, threads)
+    vals, secs = [], []
+    for _ in range(args.steps):
+        v, dt, n = cpu_reference_sample(frames, threads)
+        vals.append(v); secs.append(dt)
+    value = (SA[2] * frames * args.steps) / sum(secs)
+    sample = "%d frames x 10 slices of one synthetic SA subject per step, reference loop (batch Z per frame)" % frames
+    line = {
+        "impl": "reference", "metric": "SA FCN 192x208 slices/sec", "value": value, "unit": "slices/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SA 192x208x10x50 subjects, FCN deploy (CPU sample)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "slices/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "TF-CPU proxy (PyTorch/oneDNN float32 restatement); TensorFlow unavailable"},
+        "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("UKBB_BENCH_MODE", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--subjects", type=int, default=None, help="SA subjects per GPU per step (default 256 bf16, 2 fp32)")
+    ap.add_argument("--ref-frames", type=int, default=5)
+    ap.add_argument("--cpu-frames", type=int, default=10, help="frames in the cpu_baseline sample (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from ukbb_cardiac_b200 import synth
+    from ukbb_cardiac_b200.fcn import FCNEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S = args.subjects if args.subjects else (256 if args.mode == "bf16" else 2)
+    X, Y, Z, T = SA
+    nvox = X * Y * Z * T
+
+    eng = FCNEngine(synth.make_weights(0, 4), device=local, mode=args.mode)
+    pool = min(POOL, S)
+    host_pool = [torch.empty(nvox, dtype=torch.float32, pin_memory=True) for _ in range(pool)]
+    for i, hp in enumerate(host_pool):
+        hp.numpy()[:] = synth.make_stack(100 * rank + i).reshape(-1, order="F")
+    dev_pool = [hp.to(dev) for hp in host_pool]                 # 8 x 80 MB > 126 MB L2
+    host_labels = [torch.empty(nvox, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    host_counts = [torch.empty((Z * T, 4), dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    fwd_ev = []
+
+    def step_device(record=False):
+        for s in range(S):
+            vol = dev_pool[s % pool]
+            padded, vlvh, (xp, yp) = eng.preprocess(vol, Z * T, X, Y)
+            if record:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            eng.forward(padded, xp, yp, X, Y)
+            if record:
+                e1.record(stream)
+                fwd_ev.append((e0, e1))
+
+    def step_e2e():
+        for s in range(S):
+            eng.segment_host_async(host_pool[s % pool], SA, host_labels[s & 1], None, host_counts[s & 1])
+        eng.join()
+
+    def timed(fn, steps, **kw):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn(**kw)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    l0 = eng.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev = timed(step_device, args.steps, record=True)
+    launches = eng.launch_count - l0
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    eng.sync()
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    eng.sync()
+
+    slices = S * Z * T * args.steps * world
+    value = slices / (ms_dev * 1e-3)
+    e2e_value = slices / (ms_e2e * 1e-3)
+    fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / max(len(fwd_ev), 1)        # per 500-slice forward
+    peaks = measured_peaks()
+    achieved_tf = FLOP_PER_SLICE * Z * T / (fwd_ms * 1e-3) / 1e12
+    peak_tf = peaks["bf16_sustained"]
+    roofline = {"bound": "tensor", "kernel": "build_FCN forward (all conv launches of one 500-slice subject)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16, of measured)",
+                "frac_of_burst": achieved_tf / peaks["bf16_burst"], "frac_of_nominal_2250": achieved_tf / 2250.0,
+                "algorithmic_flop_per_slice": FLOP_PER_SLICE, "avg_forward_ms_per_subject": fwd_ms}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if args.cpu_frames > 0:
+            threads = os.cpu_count() or 1
+            v, dt, n = cpu_reference_sample(args.cpu_frames, threads)
+            cpu = {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
+                   "sample": "%d frames x 10 slices of one synthetic SA subject, reference loop (batch Z per frame), %.1f s"
+                             % (args.cpu_frames, dt),
+                   "note": "TF-CPU proxy (PyTorch/oneDNN float32 restatement); TensorFlow unavailable"}
+        line = {
+            "metric": "SA FCN 192x208 slices/sec", "value": value, "unit": "slices/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "%d synthetic SA subjects (192x208x10x50, 500 slices each) per GPU per step" % S,
+                       "subjects_per_gpu": S, "global_subjects": S * world, "mode": args.mode, "n_class": 4,
+                       "l2_policy": "inputs larger than L2: %d distinct 80 MB volumes cycled" % pool,
+                       "weights": "random-init (seed 0), reference TF checkpoint layout", "parallelism": "dp%d" % world},
+            "subjects_per_s": value / (Z * T),
+            "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": S * nvox * 4,
+                    "d2h_bytes_per_step": S * (nvox + Z * T * 4 * 8), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

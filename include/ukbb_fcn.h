@@ -1,0 +1,141 @@
+/*
+ * ukbb_fcn.h -- C ABI of the B200-native FCN segmentation engine.
+ *
+ * Drop-in boundary for the device side of ukbb_cardiac's deploy path.  Each entry
+ * point names the reference interface it replaces (paths relative to the
+ * reference repository, baiwenjia/ukbb_cardiac):
+ *
+ *   ukbb_fcn_create        <- tf.train.import_meta_graph + saver.restore
+ *                             (common/deploy_network.py:48-49): the graph is
+ *                             build_FCN (common/network.py:170-230) with the
+ *                             hyper-parameters of common/train_network.py:174-195;
+ *                             weights arrive as host float32 arrays in TF layout.
+ *   ukbb_fcn_forward       <- sess.run(['prob:0','pred:0'], feed_dict={'image:0': ...,
+ *                             'training:0': False}) (deploy_network.py:110-111, 195-196)
+ *                             fused with the transpose + crop of :114-116 / :199-200.
+ *   ukbb_fcn_preprocess    <- rescale_intensity(image, (1, 99)) (common/image_utils.py:70-77,
+ *                             called at deploy_network.py:89, 179) fused with the
+ *                             pad-to-multiple-of-16 of deploy_network.py:97-100, 185-188
+ *                             and the (X,Y,Z)->(Z,X,Y,1) float32 gather of :105-107.
+ *   ukbb_fcn_segment_host  <- one whole iteration of the per-subject body
+ *                             deploy_network.py:89-116 on HOST buffers (H2D, preprocess,
+ *                             forward over all Z*T slices, D2H of the label volume).
+ *   ukbb_fcn_class_counts  <- np.sum(pred == k, axis=(0,1,2)) of deploy_network.py:127-130
+ *                             (per-slice class histogram emitted by the classifier).
+ *
+ * Conventions
+ *   - Plain C, no torch / C++ types.  Every function returns 0 on success and a
+ *     negative UKBB_E_* code on failure; ukbb_last_error() returns a per-thread
+ *     message.  The library never calls exit() and has NO CPU fallback: without a
+ *     CUDA device every compute entry point fails with UKBB_E_CUDA.
+ *   - A handle is bound to one device and is not re-entrant; distinct handles may
+ *     be driven from distinct host threads.  All compute calls are asynchronous on
+ *     the given stream (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - Memory layout: all image-like buffers are in NIfTI memory order, X fastest:
+ *     volume [T][Z][Y][X]; padded network input [N=Z*T][Y2][X2]; labels [N][Y][X];
+ *     logits / prob [N][Y2][X2][C].  TensorFlow's NHWC view of the same slice has
+ *     H = X and W = Y; the library transposes the 3x3 kernels once at create time
+ *     instead of transposing every image.
+ */
+#ifndef UKBB_FCN_H_
+#define UKBB_FCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UKBB_OK              0
+#define UKBB_E_INVALID      -1   /* bad argument / shape */
+#define UKBB_E_CUDA         -2   /* CUDA runtime or driver error (message has the detail) */
+#define UKBB_E_NOMEM        -3
+#define UKBB_E_UNSUPPORTED  -4   /* e.g. tensor-core mode on a non-sm_100 device */
+
+/* arithmetic modes */
+#define UKBB_MODE_FP32  0   /* FP32 CUDA-core kernels: the exactness mode */
+#define UKBB_MODE_BF16  2   /* BF16 operands, FP32 accumulate on tcgen05 tensor cores */
+
+#define UKBB_N_CONV 21      /* 13 encoder 3x3 + 5 same_dim 1x1 + fc0 + fc1 + logits */
+#define UKBB_MAX_CLASS 8
+
+typedef struct ukbb_fcn ukbb_fcn;
+
+/* One tf.layers.conv2d (+ tf.layers.batch_normalization) of build_FCN, host pointers.
+ * kernel: TF HWIO [ksize][ksize][cin][cout] float32.  gamma/beta/mean/variance: [cout]
+ * or all NULL (logits layer).  bias: [cout] or NULL. */
+typedef struct {
+    const float* kernel;
+    int ksize, cin, cout, stride;
+    const float* gamma;
+    const float* beta;
+    const float* moving_mean;
+    const float* moving_variance;
+    const float* bias;
+} ukbb_conv_weights;
+
+typedef struct {
+    int n_conv;                       /* must be UKBB_N_CONV */
+    const ukbb_conv_weights* conv;    /* graph-creation order (network.py:179-229) */
+    float bn_eps;                     /* 1e-3 */
+} ukbb_fcn_weights;
+
+/* Build an engine on `device`; folds BN into per-channel scale/shift, re-lays the
+ * kernels out for the device.  The caller keeps ownership of `w`. */
+int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode, ukbb_fcn** out);
+void ukbb_fcn_destroy(ukbb_fcn* h);
+
+/* image: device float32 [n][y2][x2], already rescaled and zero-padded; x2, y2 multiples of 16.
+ * labels: device uint8 [n][y][x] = argmax over the FP32 softmax (first index on ties),
+ *         cropped at (x_pre, y_pre); required.
+ * logits, prob: optional device float32 [n][y2][x2][n_class] (NULL = not produced; the
+ *         reference fetches prob and discards it). */
+int ukbb_fcn_forward(ukbb_fcn* h, const float* image, int n, int x2, int y2,
+                     int x_pre, int y_pre, int x, int y,
+                     uint8_t* labels, float* logits, float* prob, void* stream);
+
+/* vol: device float32, n_slices*y*x voxels in NIfTI order.  Computes the exact numpy
+ * 'linear' percentiles q_lo / q_hi (in percent) over ALL voxels, then writes
+ * out[n][y2][x2] = float32((double(clip(v)) - vl) / (vh - vl)) inside the image and 0 in
+ * the padding.  vl_vh: optional device double[2] receiving (vl, vh).  If clip_in_place
+ * is non-zero `vol` itself is clipped like the reference does to its input array. */
+int ukbb_fcn_preprocess(ukbb_fcn* h, float* vol, long long n_slices, int x, int y,
+                        double q_lo, double q_hi, int x2, int y2, int x_pre, int y_pre,
+                        float* out, double* vl_vh, int clip_in_place, void* stream);
+
+/* Whole-subject call on HOST buffers (pinned for full speed): vol [T][Z][Y][X] float32 in,
+ * labels [T][Z][Y][X] uint8 out, vl_vh host double[2] out (may be NULL),
+ * counts host int64 [n_slices][n_class] out (may be NULL).  Asynchronous on `stream`:
+ * the outputs are valid after the stream (or ukbb_fcn_sync) has been synchronised.
+ * `slot` (0 or 1) selects one of two device staging buffers so consecutive subjects overlap. */
+int ukbb_fcn_segment_host(ukbb_fcn* h, const float* vol, int x, int y, int z, int t,
+                          double q_lo, double q_hi, uint8_t* labels, double* vl_vh,
+                          long long* counts, int slot, void* stream);
+
+/* Per-slice class pixel counts of the most recent ukbb_fcn_forward on this handle:
+ * counts: device int64 [n][n_class] (cropped region only). */
+int ukbb_fcn_class_counts(ukbb_fcn* h, long long* counts, int n, void* stream);
+
+/* Make `stream` wait for every outstanding read-back of ukbb_fcn_segment_host, so that an
+ * event recorded on it afterwards brackets the whole H2D -> compute -> D2H chain. */
+int ukbb_fcn_join(ukbb_fcn* h, void* stream);
+
+/* Block the host until all work of this handle's device has finished. */
+int ukbb_fcn_sync(ukbb_fcn* h);
+
+/* Introspection used by bench.py: kernels launched by this handle since creation. */
+long long ukbb_fcn_launch_count(const ukbb_fcn* h);
+int ukbb_fcn_mode(const ukbb_fcn* h);
+int ukbb_fcn_n_class(const ukbb_fcn* h);
+
+/* Host helper (no GPU): Castagnoli CRC used by the TF checkpoint bundle reader. */
+uint32_t ukbb_crc32c(const void* data, size_t n);
+
+const char* ukbb_last_error(void);
+const char* ukbb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UKBB_FCN_H_ */

@@ -1,0 +1,139 @@
+"""Checkpoint bundle, NIfTI and weight-contract tests (CPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from ukbb_cardiac_b200 import nifti, synth, tf_bundle
+from ukbb_cardiac_b200 import weights as W
+
+
+def test_crc32c_known_answers():
+    assert tf_bundle.crc32c(b"123456789") == 0xE3069283
+    assert tf_bundle.crc32c(b"") == 0
+    assert tf_bundle.crc32c(bytes(32)) == 0x8A9136AA                     # rfc3720 B.4
+    assert tf_bundle.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43
+    assert tf_bundle.unmask_crc(tf_bundle.mask_crc(0xDEADBEEF)) == 0xDEADBEEF
+
+
+def test_native_crc32c_matches_python():
+    from ukbb_cardiac_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 255, 256, 1000, 4097):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        tf_bundle.set_native_crc32c(None)
+        py = tf_bundle.crc32c(data)
+        assert int(lib.ukbb_crc32c(data, len(data))) == py
+    _lib._lib = None
+    _lib.load()
+
+
+def test_bundle_roundtrip_and_contract(tmp_path):
+    t = synth.with_optimizer_slots(synth.make_weights(0, 4))
+    t["global_step"] = np.asarray(50000, dtype=np.int64)
+    prefix = str(tmp_path / "FCN_sa")
+    tf_bundle.write_bundle(prefix, t)
+    for ext in (".index", ".data-00000-of-00001", ".meta"):
+        assert os.path.exists(prefix + ext)
+    back = tf_bundle.read_bundle(prefix)
+    assert set(back) == set(t)
+    for k in t:
+        np.testing.assert_array_equal(back[k], t[k])
+        assert back[k].dtype == t[k].dtype and back[k].shape == np.asarray(t[k]).shape
+    assert W.validate(back) == 4                      # Adam slots / global_step are ignored
+    assert W.n_parameters(4) == 1989012
+
+
+def test_bundle_detects_corruption(tmp_path):
+    t = synth.make_weights(1, 2)
+    prefix = str(tmp_path / "m")
+    tf_bundle.write_bundle(prefix, t)
+    data = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    data[1234] ^= 0x40
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+    with pytest.raises(ValueError, match="checksum"):
+        tf_bundle.read_bundle(prefix)
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    idx[-1] ^= 0xFF
+    open(prefix + ".index", "wb").write(bytes(idx))
+    with pytest.raises(ValueError, match="magic"):
+        tf_bundle.read_bundle(prefix)
+
+
+def test_validate_fails_loudly():
+    t = synth.make_weights(0, 3)
+    assert W.validate(t) == 3
+    bad = dict(t); del bad["batch_normalization_7/gamma"]
+    with pytest.raises(KeyError):
+        W.validate(bad)
+    bad = dict(t); bad["conv2d_5/kernel"] = np.zeros((3, 3, 64, 32), np.float32)
+    with pytest.raises(ValueError):
+        W.validate(bad)
+    with pytest.raises(KeyError):
+        W.validate({"foo": np.zeros(1, np.float32)})
+    # n_class is inferred from the last kernel (seg4 model: 6 classes)
+    assert W.validate(synth.make_weights(0, 6)) == 6
+
+
+def test_layer_table_names():
+    assert W.conv_name(0) == "conv2d" and W.conv_name(20) == "conv2d_20"
+    assert W.bn_name(0) == "batch_normalization" and W.bn_name(19) == "batch_normalization_19"
+    shapes = W.expected_shapes(4)
+    assert shapes["conv2d/kernel"] == (3, 3, 1, 16)
+    assert shapes["conv2d_13/kernel"] == (1, 1, 16, 32)
+    assert shapes["conv2d_18/kernel"] == (1, 1, 160, 64)
+    assert shapes["conv2d_20/bias"] == (4,)
+    assert "batch_normalization_20/gamma" not in shapes
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int16, np.float64, np.uint8])
+def test_nifti_roundtrip(tmp_path, dtype):
+    rng = np.random.default_rng(2)
+    data = np.asfortranarray((rng.random((7, 5, 3, 2)) * 100).astype(dtype))
+    aff = np.array([[-1.8, 0, 0, 90.0], [0, 1.8, 0.1, -120.0], [0, -0.1, 10.0, 33.0], [0, 0, 0, 1]])
+    img = nifti.Nifti1Image(data, aff)
+    img.header["pixdim"][4] = 0.031
+    p = str(tmp_path / "sa.nii.gz")
+    nifti.save(img, p)
+    back = nifti.load(p)
+    np.testing.assert_array_equal(back.get_data(), data)
+    assert back.get_data().dtype == dtype and back.get_data().flags.f_contiguous
+    np.testing.assert_allclose(back.affine, aff, rtol=1e-6)
+    assert back.header["pixdim"][4] == np.float32(0.031)
+    np.testing.assert_allclose(back.header["pixdim"][1:4], [1.8, np.sqrt(1.8 ** 2 + 0.1 ** 2), np.sqrt(0.1 ** 2 + 100)], rtol=1e-6)
+
+
+def test_nifti_label_volume_like_reference(tmp_path):
+    """deploy_network.py:134-137: Nifti1Image(pred float64, nim.affine) + pixdim copy."""
+    src = nifti.Nifti1Image(np.zeros((4, 4, 2, 3), np.float32, order="F"), np.diag([1.8, 1.8, 10.0, 1.0]))
+    src.header["pixdim"][4] = 0.05
+    pred = np.asfortranarray(np.random.default_rng(0).integers(0, 4, (4, 4, 2, 3)).astype(np.float64))
+    out = nifti.Nifti1Image(pred, src.affine)
+    out.header["pixdim"] = src.header["pixdim"]
+    p = str(tmp_path / "seg_sa.nii.gz")
+    nifti.save(out, p)
+    back = nifti.load(p)
+    assert back.get_data().dtype == np.float64
+    np.testing.assert_array_equal(back.get_data(), pred)
+    np.testing.assert_array_equal(back.header["pixdim"], src.header["pixdim"])
+    np.testing.assert_allclose(back.affine, src.affine)
+    # plain .nii and scl_slope handling
+    src.header["scl_slope"], src.header["scl_inter"] = 2.0, 1.0
+    nifti.save(src, str(tmp_path / "x.nii"))
+    np.testing.assert_array_equal(nifti.load(str(tmp_path / "x.nii")).get_data(), np.ones((4, 4, 2, 3)))
+
+
+def test_nifti_rejects_garbage(tmp_path):
+    p = str(tmp_path / "bad.nii")
+    open(p, "wb").write(b"\x00" * 400)
+    with pytest.raises(ValueError):
+        nifti.load(p)
+
+
+def test_synth_stack_properties():
+    v = synth.make_stack(3, (32, 48, 2, 3))
+    assert v.shape == (32, 48, 2, 3) and v.dtype == np.float32 and v.flags.f_contiguous
+    assert np.all(v == np.rint(v)) and v.min() >= 0 and v.max() <= 4095
+    np.testing.assert_array_equal(v, synth.make_stack(3, (32, 48, 2, 3)))
+    assert not np.array_equal(v, synth.make_stack(4, (32, 48, 2, 3)))

@@ -1,0 +1,247 @@
+// Preprocessing kernels (north_star (d)): exact percentile intensity rescale + pad to x16.
+// Restates common/image_utils.py:70-77 (rescale_intensity) as it executes under numpy 2:
+//   vl, vh = np.percentile(image, (1, 99))      method 'linear', float64 result; for float32
+//                                               input numpy lerps a + f32(b - a) * t in double
+//                                               (b - f32(b - a) * (1 - t) when t >= 0.5)
+//   image[image < vl] = vl; image[image > vh] = vh      (in place, rounded to float32)
+//   out = (float32(image) - vl) / (vh - vl)             (double arithmetic)
+// and common/deploy_network.py:97-107 (zero pad to multiples of 16, float32 cast).
+//
+// The order statistics are found EXACTLY by a 3-pass most-significant-digit radix select
+// (12 + 12 + 8 bits) over the order-preserving integer image of the float32 bit pattern;
+// all four ranks (floor/ceil of both percentiles) are resolved together so the volume is
+// read three times for the select and once for the rescale (an SA volume, 80 MB, stays
+// resident in the 126 MB L2 between passes).  HBM-bound integer/byte work: coalesced
+// 128-bit loads, shared-memory histograms, no tensor cores.
+#include "common.cuh"
+#include <math.h>
+
+namespace ukbb {
+
+constexpr int NRANK = 4;
+constexpr int BINS0 = 4096, BINS1 = 4096, BINS2 = 256;
+// hist layout: [pass0: 4096][pass1: 4 x 4096][pass2: 4 x 256]
+constexpr int HIST_WORDS = BINS0 + NRANK * BINS1 + NRANK * BINS2;
+
+struct SelState {                 // device-resident select state
+    unsigned long long rank[NRANK];     // residual rank inside the current prefix
+    unsigned int prefix[NRANK];         // key prefix resolved so far (12 then 24 then 32 bits)
+};
+
+__device__ __forceinline__ unsigned int f2key(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned int k) {
+    const unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+__global__ void sel_init_kernel(SelState* st, unsigned int* hist, unsigned long long r0,
+                                unsigned long long r1, unsigned long long r2, unsigned long long r3) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HIST_WORDS; i += gridDim.x * blockDim.x) hist[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->rank[0] = r0; st->rank[1] = r1; st->rank[2] = r2; st->rank[3] = r3;
+        for (int r = 0; r < NRANK; ++r) st->prefix[r] = 0;
+    }
+}
+
+// PASS 0: 4096-bin histogram of key >> 20, shared-memory privatised.  Each thread folds runs of
+// equal bins among its own consecutive voxels before touching shared memory (neighbouring
+// voxels of an MR image mostly share the top 12 key bits).
+__global__ void __launch_bounds__(512)
+sel_hist0_kernel(const float* __restrict__ vol, long long n, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[BINS0];
+    for (int i = threadIdx.x; i < BINS0; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const long long n4 = n >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(vol);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(v4 + i);
+        const unsigned int b0 = f2key(v.x) >> 20, b1 = f2key(v.y) >> 20, b2 = f2key(v.z) >> 20,
+                           b3 = f2key(v.w) >> 20;
+        if (b0 == b1 && b1 == b2 && b2 == b3) {
+            atomicAdd(&sh[b0], 4u);
+        } else {
+            atomicAdd(&sh[b0], 1u); atomicAdd(&sh[b1], 1u); atomicAdd(&sh[b2], 1u); atomicAdd(&sh[b3], 1u);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) atomicAdd(&sh[f2key(vol[(n4 << 2) + threadIdx.x]) >> 20], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < BINS0; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// PASS 1 / 2: voxels whose resolved prefix matches one of the four ranks vote on the next digit.
+// Matches are ~1/4096 of the voxels for natural images, so they go to global atomics directly.
+template <int PASS>
+__global__ void __launch_bounds__(512)
+sel_histn_kernel(const float* __restrict__ vol, long long n, const SelState* __restrict__ st,
+                 unsigned int* __restrict__ hist) {
+    unsigned int pre[NRANK];
+#pragma unroll
+    for (int r = 0; r < NRANK; ++r) pre[r] = st->prefix[r];
+    constexpr int SHIFT = PASS == 1 ? 20 : 8;
+    auto vote = [&](float f) {
+        const unsigned int k = f2key(f);
+        const unsigned int p = k >> SHIFT;
+#pragma unroll
+        for (int r = 0; r < NRANK; ++r) {
+            if (p == pre[r]) {
+                // identical prefixes share the work: later ranks with the same prefix read rank r's bins
+                bool first = true;
+#pragma unroll
+                for (int q = 0; q < r; ++q) first = first && (pre[q] != pre[r]);
+                if (first) {
+                    if (PASS == 1) atomicAdd(&hist[BINS0 + r * BINS1 + ((k >> 8) & 0xFFFu)], 1u);
+                    else atomicAdd(&hist[BINS0 + NRANK * BINS1 + r * BINS2 + (k & 0xFFu)], 1u);
+                }
+            }
+        }
+    };
+    const long long n4 = n >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(vol);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(v4 + i);
+        vote(v.x); vote(v.y); vote(v.z); vote(v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) vote(vol[(n4 << 2) + threadIdx.x]);
+}
+
+// After each pass: locate, for every rank, the bin holding it (one warp per rank, serial scan by
+// lane 0 is plenty: <= 4096 bins).  Ranks that share a prefix share the histogram of the first.
+template <int PASS>
+__global__ void sel_scan_kernel(SelState* st, const unsigned int* __restrict__ hist) {
+    const int r = threadIdx.x;          // launched with one warp; lanes >= NRANK idle
+    unsigned int pre[NRANK];
+    for (int q = 0; q < NRANK; ++q) pre[q] = st->prefix[q];
+    __syncwarp();                       // every lane has read the prefixes before any update
+    if (r < NRANK) {
+        int src = r;
+        if (PASS > 0)
+            for (int q = r - 1; q >= 0; --q)
+                if (pre[q] == pre[r]) src = q;
+        const unsigned int* h = PASS == 0 ? hist : PASS == 1 ? hist + BINS0 + src * BINS1
+                                                             : hist + BINS0 + NRANK * BINS1 + src * BINS2;
+        const int bins = PASS == 2 ? BINS2 : BINS0;
+        const unsigned long long want = st->rank[r];
+        unsigned long long cum = 0;
+        int b = 0;
+        for (; b < bins - 1; ++b) {
+            const unsigned int c = h[b];
+            if (cum + c > want) break;
+            cum += c;
+        }
+        st->rank[r] = want - cum;
+        st->prefix[r] = PASS == 0 ? (unsigned)b : PASS == 1 ? ((pre[r] << 12) | (unsigned)b)
+                                                            : ((pre[r] << 8) | (unsigned)b);
+    }
+}
+
+__global__ void sel_final_kernel(const SelState* __restrict__ st, double t_lo, double t_hi,
+                                 double* __restrict__ vlvh, float* __restrict__ sel, double* vlvh_user) {
+    if (threadIdx.x != 0) return;
+    float v[NRANK];
+    for (int r = 0; r < NRANK; ++r) { v[r] = key2f(st->prefix[r]); sel[r] = v[r]; }
+    // numpy _lerp on float32 neighbours: diff in float32, interpolation in float64
+    auto lerp = [](float a, float b, double t) {
+        const float diff = b - a;
+        return t >= 0.5 ? (double)b - (double)diff * (1.0 - t) : (double)a + (double)diff * t;
+    };
+    const double vl = lerp(v[0], v[1], t_lo), vh = lerp(v[2], v[3], t_hi);
+    vlvh[0] = vl; vlvh[1] = vh;
+    if (vlvh_user) { vlvh_user[0] = vl; vlvh_user[1] = vh; }
+}
+
+// Rescale + zero-pad: one thread = 4 consecutive output pixels along X of the padded slice.
+__global__ void __launch_bounds__(256)
+rescale_pad_kernel(float* __restrict__ vol, float* __restrict__ out, const double* __restrict__ vlvh,
+                   long long total4, int x, int y, int x2, int y2, int x_pre, int y_pre, int clip_in_place) {
+    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const double vl = vlvh[0], vh = vlvh[1];
+    const float fl = (float)vl, fh = (float)vh;     // what `image[image < vl] = vl` stores
+    const double den = vh - vl;
+    const int xq = x2 >> 2;
+    const int ox = (int)(i4 % xq) * 4;
+    const int oy = (int)((i4 / xq) % y2);
+    const long long n = i4 / ((long long)xq * y2);
+    const int sy = oy - y_pre;
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sy >= 0 && sy < y) {
+        float* row = vol + (n * y + sy) * (long long)x;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int sx = ox + u - x_pre;
+            if (sx >= 0 && sx < x) {
+                float v = row[sx];
+                // comparisons against the float64 thresholds, like numpy's float32-vs-float64 compare
+                if ((double)v < vl) v = fl;
+                if ((double)v > vh) v = fh;
+                if (clip_in_place) row[sx] = v;
+                r[u] = (float)(((double)v - vl) / den);
+            }
+        }
+    }
+    reinterpret_cast<float4*>(out)[i4] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+int preproc_alloc(PreprocWorkspace& ws) {
+    UKBB_CUDA(cudaMalloc(&ws.hist, HIST_WORDS * sizeof(unsigned int)));
+    UKBB_CUDA(cudaMalloc(&ws.state, sizeof(SelState)));
+    UKBB_CUDA(cudaMalloc(&ws.vlvh, 2 * sizeof(double)));
+    UKBB_CUDA(cudaMalloc(&ws.sel, NRANK * sizeof(float)));
+    return UKBB_OK;
+}
+
+void preproc_free(PreprocWorkspace& ws) {
+    cudaFree(ws.hist); cudaFree(ws.state); cudaFree(ws.vlvh); cudaFree(ws.sel);
+    ws = PreprocWorkspace();
+}
+
+int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int x, int y, double q_lo,
+                      double q_hi, int x2, int y2, int x_pre, int y_pre, float* out, double* vl_vh_out,
+                      int clip_in_place, cudaStream_t st, long long* launches) {
+    const long long n = n_slices * x * y;
+    UKBB_REQUIRE(n > 0, "preprocess: empty volume");
+    UKBB_REQUIRE(x2 % 16 == 0 && y2 % 16 == 0 && x2 >= x + x_pre && y2 >= y + y_pre && x_pre >= 0 && y_pre >= 0,
+                 "preprocess: bad padded size %dx%d for %dx%d pre (%d,%d)", x2, y2, x, y, x_pre, y_pre);
+    UKBB_REQUIRE(((uintptr_t)vol & 15) == 0 && ((uintptr_t)out & 15) == 0, "preprocess: buffers must be 16-byte aligned");
+    // numpy 'linear': virtual index (n-1)*q/100, neighbours floor / floor+1 (clipped), gamma = frac
+    double t[2];
+    unsigned long long rk[4];
+    const double qs[2] = {q_lo, q_hi};
+    for (int i = 0; i < 2; ++i) {
+        UKBB_REQUIRE(qs[i] >= 0.0 && qs[i] <= 100.0, "preprocess: percentile %g outside [0,100]", qs[i]);
+        const double vi = (double)(n - 1) * (qs[i] / 100.0);
+        const double fl = floor(vi);
+        t[i] = vi - fl;
+        unsigned long long lo = (unsigned long long)fl;
+        if (lo > (unsigned long long)(n - 1)) lo = n - 1;
+        unsigned long long hi = lo + 1 > (unsigned long long)(n - 1) ? (unsigned long long)(n - 1) : lo + 1;
+        rk[2 * i] = lo; rk[2 * i + 1] = hi;
+    }
+    SelState* state = reinterpret_cast<SelState*>(ws.state);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int hgrid = sms * 4;       // 4 resident 512-thread CTAs per SM
+    sel_init_kernel<<<16, 256, 0, st>>>(state, ws.hist, rk[0], rk[1], rk[2], rk[3]);
+    sel_hist0_kernel<<<hgrid, 512, 0, st>>>(vol, n, ws.hist);
+    sel_scan_kernel<0><<<1, 32, 0, st>>>(state, ws.hist);
+    sel_histn_kernel<1><<<hgrid, 512, 0, st>>>(vol, n, state, ws.hist);
+    sel_scan_kernel<1><<<1, 32, 0, st>>>(state, ws.hist);
+    sel_histn_kernel<2><<<hgrid, 512, 0, st>>>(vol, n, state, ws.hist);
+    sel_scan_kernel<2><<<1, 32, 0, st>>>(state, ws.hist);
+    sel_final_kernel<<<1, 32, 0, st>>>(state, t[0], t[1], ws.vlvh, ws.sel, vl_vh_out);
+    const long long total4 = n_slices * y2 * (x2 / 4);
+    rescale_pad_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(vol, out, ws.vlvh, total4, x, y, x2, y2,
+                                                                          x_pre, y_pre, clip_in_place);
+    if (launches) *launches += 9;
+    UKBB_CUDA(cudaGetLastError());
+    return UKBB_OK;
+}
+
+}  // namespace ukbb

@@ -1,0 +1,229 @@
+"""Host-side engine: the Python mirror of the reference's operator boundary.
+
+The reference drives the network through
+``sess.run(['prob:0', 'pred:0'], feed_dict={'image:0': image, 'training:0': False})``
+(``common/deploy_network.py:110-111, 195-196``) after restoring the graph with
+``tf.train.import_meta_graph`` / ``saver.restore`` (``:48-49``).  ``FCNEngine`` keeps
+those names and argument meanings (``Session``-style ``run``), and adds the
+whole-volume calls the B200 design is built around (one call per subject
+instead of one per frame).  PyTorch is used only to own device / pinned
+memory and streams; every kernel lives in libukbb_fcn.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, tf_bundle
+from . import weights as W
+
+MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}
+
+
+def pad16(x: int) -> Tuple[int, int]:
+    """deploy_network.py:97-98 -> (X2, x_pre)."""
+    x2 = int(math.ceil(x / 16.0)) * 16
+    return x2, int((x2 - x) / 2)
+
+
+def _fptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class FCNEngine:
+    """build_FCN inference engine bound to one CUDA device."""
+
+    def __init__(self, tensors: Dict[str, np.ndarray], device: int = 0, mode: str = "bf16"):
+        if mode not in MODES:
+            raise ValueError("mode must be one of %s" % sorted(MODES))
+        if not torch.cuda.is_available():
+            raise RuntimeError("FCNEngine needs a CUDA device: libukbb_fcn has no CPU fallback")
+        self.lib = _lib.load()
+        self.n_class = W.validate(tensors)
+        self.mode = mode
+        self.device = torch.device("cuda", device)
+        tab = W.layer_table(self.n_class)
+        keep = []          # keep host arrays alive during the create call
+        convs = (_lib.ConvWeights * W.N_CONV)()
+        for i, sp in enumerate(tab):
+            k = np.ascontiguousarray(tensors[W.conv_name(i) + "/kernel"], dtype=np.float32)
+            keep.append(k)
+            cw = convs[i]
+            cw.kernel = _fptr(k)
+            cw.ksize, cw.cin, cw.cout, cw.stride = sp.ksize, sp.cin, sp.cout, sp.stride
+            if i < W.N_BN:
+                arrs = [np.ascontiguousarray(tensors[W.bn_name(i) + "/" + v], dtype=np.float32)
+                        for v in ("gamma", "beta", "moving_mean", "moving_variance")]
+                keep.extend(arrs)
+                cw.gamma, cw.beta, cw.moving_mean, cw.moving_variance = (_fptr(a) for a in arrs)
+            else:
+                b = np.ascontiguousarray(tensors[W.conv_name(i) + "/bias"], dtype=np.float32)
+                keep.append(b)
+                cw.bias = _fptr(b)
+        fw = _lib.FcnWeights(W.N_CONV, convs, W.BN_EPS)
+        handle = C.c_void_p()
+        _lib.check(self.lib.ukbb_fcn_create(C.byref(fw), self.n_class, device, MODES[mode], C.byref(handle)))
+        self._h = handle
+        self._slot = 0
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_checkpoint(cls, model_path: str, device: int = 0, mode: str = "bf16") -> "FCNEngine":
+        """``saver.restore(sess, model_path)``: reads ``model_path.index`` / ``.data-*``."""
+        _lib.load()
+        tensors = tf_bundle.read_bundle(model_path)
+        return cls(tensors, device=device, mode=mode)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.ukbb_fcn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ device-level calls
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def forward(self, image: torch.Tensor, x_pre: int = 0, y_pre: int = 0, x: Optional[int] = None,
+                y: Optional[int] = None, want_logits: bool = False, want_prob: bool = False):
+        """image: cuda float32 [N, Y2, X2] (rescaled, padded).  Returns (labels uint8 [N, Y, X],
+        logits or None, prob or None) with logits/prob as [N, Y2, X2, C]."""
+        assert image.is_cuda and image.dtype == torch.float32 and image.dim() == 3 and image.is_contiguous()
+        n, y2, x2 = image.shape
+        x = x2 - x_pre if x is None else x
+        y = y2 - y_pre if y is None else y
+        labels = torch.empty((n, y, x), dtype=torch.uint8, device=self.device)
+        logits = torch.empty((n, y2, x2, self.n_class), dtype=torch.float32, device=self.device) if want_logits else None
+        prob = torch.empty((n, y2, x2, self.n_class), dtype=torch.float32, device=self.device) if want_prob else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ukbb_fcn_forward(
+                self._h, image.data_ptr(), n, x2, y2, x_pre, y_pre, x, y, labels.data_ptr(),
+                logits.data_ptr() if want_logits else None, prob.data_ptr() if want_prob else None, self._stream()))
+        return labels, logits, prob
+
+    def class_counts(self, n: int) -> torch.Tensor:
+        out = torch.empty((n, self.n_class), dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.ukbb_fcn_class_counts(self._h, out.data_ptr(), n, self._stream()))
+        return out
+
+    def preprocess(self, vol: torch.Tensor, n_slices: int, x: int, y: int, q: Sequence[float] = (1.0, 99.0),
+                   clip_in_place: bool = False):
+        """vol: cuda float32 with n_slices*y*x voxels in NIfTI order.  Returns (padded [N, Y2, X2]
+        float32, vl_vh cuda float64[2], (x_pre, y_pre))."""
+        assert vol.is_cuda and vol.dtype == torch.float32 and vol.is_contiguous() and vol.numel() == n_slices * x * y
+        x2, x_pre = pad16(x)
+        y2, y_pre = pad16(y)
+        out = torch.empty((n_slices, y2, x2), dtype=torch.float32, device=self.device)
+        vlvh = torch.empty(2, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ukbb_fcn_preprocess(
+                self._h, vol.data_ptr(), n_slices, x, y, float(q[0]), float(q[1]), x2, y2, x_pre, y_pre,
+                out.data_ptr(), vlvh.data_ptr(), int(clip_in_place), self._stream()))
+        return out, vlvh, (x_pre, y_pre)
+
+    # ------------------------------------------------------------------ host-level calls
+    def segment_host_async(self, vol: torch.Tensor, shape: Tuple[int, int, int, int], labels: torch.Tensor,
+                           vl_vh: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+                           q: Sequence[float] = (1.0, 99.0)) -> None:
+        """Whole-subject call on (pinned) HOST tensors: vol float32 with X*Y*Z*T voxels in NIfTI
+        order, labels uint8 of the same size.  Asynchronous; alternate staging slots are used so
+        consecutive subjects overlap H2D / compute / D2H.  Call ``sync()`` before reading."""
+        x, y, z, t = shape
+        assert not vol.is_cuda and vol.dtype == torch.float32 and vol.is_contiguous() and vol.numel() == x * y * z * t
+        assert not labels.is_cuda and labels.dtype == torch.uint8 and labels.is_contiguous() and labels.numel() == vol.numel()
+        if vl_vh is not None:
+            assert vl_vh.dtype == torch.float64 and vl_vh.numel() >= 2 and not vl_vh.is_cuda
+        if counts is not None:
+            assert counts.dtype == torch.int64 and counts.numel() >= z * t * self.n_class and not counts.is_cuda
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ukbb_fcn_segment_host(
+                self._h, vol.data_ptr(), x, y, z, t, float(q[0]), float(q[1]), labels.data_ptr(),
+                vl_vh.data_ptr() if vl_vh is not None else None,
+                counts.data_ptr() if counts is not None else None, self._slot, self._stream()))
+        self._slot ^= 1
+
+    def join(self) -> None:
+        _lib.check(self.lib.ukbb_fcn_join(self._h, self._stream()))
+
+    def sync(self) -> None:
+        _lib.check(self.lib.ukbb_fcn_sync(self._h))
+
+    def segment_volume(self, image: np.ndarray, q: Sequence[float] = (1.0, 99.0)):
+        """image: (X, Y, Z, T), (X, Y, Z) or (X, Y) array as returned by ``nim.get_data()``.
+        Returns (labels uint8 array of the same shape, Fortran order, (vl, vh), counts
+        int64 [T, Z, n_class])."""
+        shp = tuple(image.shape)
+        if image.ndim == 2:
+            x, y, z, t = shp[0], shp[1], 1, 1
+        elif image.ndim == 3:
+            x, y, z, t = shp[0], shp[1], shp[2], 1
+        elif image.ndim == 4:
+            x, y, z, t = shp
+        else:
+            raise ValueError("expected a 2-D, 3-D or 4-D image, got shape %s" % (shp,))
+        n = x * y * z * t
+        vol = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        # NIfTI memory order = Fortran order of the (X, Y, Z, T) array
+        vol.numpy()[:] = np.asarray(image, dtype=np.float32).reshape(-1, order="F")
+        labels = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        vlvh = torch.empty(2, dtype=torch.float64, pin_memory=True)
+        counts = torch.empty((t, z, self.n_class), dtype=torch.int64, pin_memory=True)
+        self.segment_host_async(vol, (x, y, z, t), labels, vlvh, counts, q)
+        self.sync()
+        lab = labels.numpy().reshape(shp, order="F").copy(order="F")
+        return lab, (float(vlvh[0]), float(vlvh[1])), counts.numpy().copy()
+
+    # ------------------------------------------------------------------ reference operator API
+    def run(self, fetches, feed_dict):
+        """Drop-in for ``sess.run(['prob:0', 'pred:0'], feed_dict={'image:0': image_NXYC,
+        'training:0': False})``: returns the fetched arrays in TF's layouts
+        (prob float32 [N, X, Y, C], pred int32 [N, X, Y])."""
+        single = isinstance(fetches, str)
+        names = [fetches] if single else list(fetches)
+        for nm in names:
+            if nm not in ("prob:0", "pred:0", "logits:0"):
+                raise KeyError("unknown fetch %r (the deploy graph exposes prob:0 and pred:0)" % nm)
+        if "image:0" not in feed_dict:
+            raise KeyError("feed_dict must provide 'image:0'")
+        if feed_dict.get("training:0", False):
+            raise NotImplementedError("training:0=True (batch statistics) is not part of the deploy path")
+        img = np.asarray(feed_dict["image:0"], dtype=np.float32)
+        if img.ndim != 4 or img.shape[3] != 1:
+            raise ValueError("image:0 must have shape [N, X, Y, 1], got %s" % (img.shape,))
+        n, xx, yy, _ = img.shape
+        if xx % 16 or yy % 16:
+            raise ValueError("image:0 spatial size %dx%d must be a multiple of 16 "
+                             "(deploy_network.py:97-100 pads before calling)" % (xx, yy))
+        dev = torch.from_numpy(np.ascontiguousarray(img[..., 0])).to(self.device)      # [N, X, Y]
+        dev = dev.permute(0, 2, 1).contiguous()                                          # [N, Y, X]
+        labels, logits, prob = self.forward(dev, want_logits="logits:0" in names, want_prob="prob:0" in names)
+        out = []
+        for nm in names:
+            if nm == "pred:0":
+                out.append(labels.permute(0, 2, 1).to(torch.int32).cpu().numpy())
+            elif nm == "prob:0":
+                out.append(prob.permute(0, 2, 1, 3).contiguous().cpu().numpy())
+            else:
+                out.append(logits.permute(0, 2, 1, 3).contiguous().cpu().numpy())
+        return out[0] if single else out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ukbb_fcn_launch_count(self._h))

@@ -1,0 +1,216 @@
+"""Minimal NIfTI-1 single-file (.nii / .nii.gz) reader and writer.
+
+The reference does all image I/O through nibabel (``common/deploy_network.py:
+80-82,134-151``: ``nib.load``, ``get_data``, ``Nifti1Image(pred, nim.affine)``,
+``header['pixdim']`` copy, ``nib.save``).  nibabel is not available in the build
+or GPU image, so this module provides exactly the subset the deploy path needs,
+with nibabel's conventions: data in Fortran (X-fastest) order, best affine =
+sform if sform_code > 0 else qform if qform_code > 0 else pixdim scaling, a new
+image gets sform_code=2 / qform_code=0, scl_slope/inter applied on read when valid.
+"""
+from __future__ import annotations
+
+import gzip
+import io
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HDR = np.dtype([
+    ("sizeof_hdr", "<i4"), ("data_type", "S10"), ("db_name", "S18"), ("extents", "<i4"),
+    ("session_error", "<i2"), ("regular", "S1"), ("dim_info", "u1"),
+    ("dim", "<i2", (8,)), ("intent_p1", "<f4"), ("intent_p2", "<f4"), ("intent_p3", "<f4"),
+    ("intent_code", "<i2"), ("datatype", "<i2"), ("bitpix", "<i2"), ("slice_start", "<i2"),
+    ("pixdim", "<f4", (8,)), ("vox_offset", "<f4"), ("scl_slope", "<f4"), ("scl_inter", "<f4"),
+    ("slice_end", "<i2"), ("slice_code", "u1"), ("xyzt_units", "u1"),
+    ("cal_max", "<f4"), ("cal_min", "<f4"), ("slice_duration", "<f4"), ("toffset", "<f4"),
+    ("glmax", "<i4"), ("glmin", "<i4"), ("descrip", "S80"), ("aux_file", "S24"),
+    ("qform_code", "<i2"), ("sform_code", "<i2"),
+    ("quatern_b", "<f4"), ("quatern_c", "<f4"), ("quatern_d", "<f4"),
+    ("qoffset_x", "<f4"), ("qoffset_y", "<f4"), ("qoffset_z", "<f4"),
+    ("srow_x", "<f4", (4,)), ("srow_y", "<f4", (4,)), ("srow_z", "<f4", (4,)),
+    ("intent_name", "S16"), ("magic", "S4"),
+])
+assert _HDR.itemsize == 348
+
+_CODE2DT = {2: np.uint8, 4: np.int16, 8: np.int32, 16: np.float32, 64: np.float64,
+            256: np.int8, 512: np.uint16, 768: np.uint32, 1024: np.int64, 1280: np.uint64}
+_DT2CODE = {np.dtype(v): k for k, v in _CODE2DT.items()}
+
+
+def _quat_to_affine(h) -> np.ndarray:
+    b, c, d = float(h["quatern_b"]), float(h["quatern_c"]), float(h["quatern_d"])
+    a2 = 1.0 - (b * b + c * c + d * d)
+    a = np.sqrt(a2) if a2 > 1e-7 else 0.0
+    if a2 <= 1e-7:
+        nrm = 1.0 / np.sqrt(b * b + c * c + d * d)
+        b, c, d = b * nrm, c * nrm, d * nrm
+    R = np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                  [2 * (b * c + a * d), a * a + c * c - b * b - d * d, 2 * (c * d - a * b)],
+                  [2 * (b * d - a * c), 2 * (c * d + a * b), a * a + d * d - b * b - c * c]])
+    pd = np.asarray(h["pixdim"], dtype=np.float64)
+    qfac = -1.0 if pd[0] < 0 else 1.0
+    zooms = np.where(pd[1:4] > 0, pd[1:4], 1.0)
+    aff = np.eye(4)
+    aff[:3, :3] = R * (zooms * np.array([1.0, 1.0, qfac]))[None, :]
+    aff[:3, 3] = [h["qoffset_x"], h["qoffset_y"], h["qoffset_z"]]
+    return aff
+
+
+def _affine_to_quat(aff: np.ndarray) -> Tuple[float, float, float, float, np.ndarray]:
+    """nifti1 mat44_to_quatern (orthonormalisation skipped: rotation taken from the
+    column-normalised matrix).  Returns (b, c, d, qfac, zooms)."""
+    M = np.asarray(aff, dtype=np.float64)[:3, :3]
+    zooms = np.sqrt((M * M).sum(axis=0))
+    zooms = np.where(zooms > 0, zooms, 1.0)
+    R = M / zooms[None, :]
+    qfac = 1.0
+    if np.linalg.det(R) < 0:
+        R[:, 2] = -R[:, 2]
+        qfac = -1.0
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    a = tr + 1.0
+    if a > 0.5:
+        a = 0.5 * np.sqrt(a)
+        b = 0.25 * (R[2, 1] - R[1, 2]) / a
+        c = 0.25 * (R[0, 2] - R[2, 0]) / a
+        d = 0.25 * (R[1, 0] - R[0, 1]) / a
+    else:
+        xd, yd, zd = 1 + R[0, 0] - (R[1, 1] + R[2, 2]), 1 + R[1, 1] - (R[0, 0] + R[2, 2]), 1 + R[2, 2] - (R[0, 0] + R[1, 1])
+        if xd > 1.0:
+            b = 0.5 * np.sqrt(xd); c = 0.25 * (R[0, 1] + R[1, 0]) / b; d = 0.25 * (R[0, 2] + R[2, 0]) / b; a = 0.25 * (R[2, 1] - R[1, 2]) / b
+        elif yd > 1.0:
+            c = 0.5 * np.sqrt(yd); b = 0.25 * (R[0, 1] + R[1, 0]) / c; d = 0.25 * (R[1, 2] + R[2, 1]) / c; a = 0.25 * (R[0, 2] - R[2, 0]) / c
+        else:
+            d = 0.5 * np.sqrt(zd); b = 0.25 * (R[0, 2] + R[2, 0]) / d; c = 0.25 * (R[1, 2] + R[2, 1]) / d; a = 0.25 * (R[1, 0] - R[0, 1]) / d
+        if a < 0:
+            b, c, d = -b, -c, -d
+    return float(b), float(c), float(d), qfac, zooms
+
+
+class Nifti1Image:
+    """The slice of nibabel's ``Nifti1Image`` used by deploy_network.py."""
+
+    def __init__(self, data: np.ndarray, affine: Optional[np.ndarray], header: Optional[np.ndarray] = None):
+        self._data = data
+        if header is None:
+            header = np.zeros((), dtype=_HDR)
+            header["sizeof_hdr"] = 348
+            header["regular"] = b"r"
+            header["pixdim"] = 1.0
+            header["vox_offset"] = 352.0
+            header["scl_slope"] = np.nan
+            header["scl_inter"] = np.nan
+            header["magic"] = b"n+1"
+            if affine is None:
+                affine = np.eye(4)
+            affine = np.asarray(affine, dtype=np.float64)
+            b, c, d, qfac, zooms = _affine_to_quat(affine)
+            header["pixdim"][0] = qfac
+            nd = min(data.ndim, 3)
+            header["pixdim"][1:1 + nd] = zooms[:nd]
+            header["quatern_b"], header["quatern_c"], header["quatern_d"] = b, c, d
+            header["qoffset_x"], header["qoffset_y"], header["qoffset_z"] = affine[:3, 3]
+            header["qform_code"] = 0
+            header["sform_code"] = 2
+            header["srow_x"], header["srow_y"], header["srow_z"] = affine[0], affine[1], affine[2]
+        else:
+            header = header.copy()
+            if affine is not None:
+                affine = np.asarray(affine, dtype=np.float64)
+        self.header = header
+        self._affine = affine if affine is not None else self._best_affine()
+        self._sync_shape()
+
+    def _sync_shape(self):
+        d = self._data
+        if d.ndim > 7:
+            raise ValueError("NIfTI-1 supports at most 7 dimensions")
+        dim = np.ones(8, dtype=np.int16)
+        dim[0] = d.ndim
+        dim[1:1 + d.ndim] = d.shape
+        self.header["dim"] = dim
+        dt = np.dtype(d.dtype).newbyteorder("=")
+        if dt not in _DT2CODE:
+            raise TypeError("dtype %s cannot be stored in NIfTI-1 by this writer" % d.dtype)
+        self.header["datatype"] = _DT2CODE[dt]
+        self.header["bitpix"] = dt.itemsize * 8
+
+    def _best_affine(self) -> np.ndarray:
+        h = self.header
+        if int(h["sform_code"]) > 0:
+            aff = np.eye(4)
+            aff[0], aff[1], aff[2] = h["srow_x"], h["srow_y"], h["srow_z"]
+            return aff
+        if int(h["qform_code"]) > 0:
+            return _quat_to_affine(h)
+        pd = np.asarray(h["pixdim"], dtype=np.float64)
+        aff = np.diag([pd[1] or 1.0, pd[2] or 1.0, pd[3] or 1.0, 1.0])
+        return aff
+
+    @property
+    def affine(self) -> np.ndarray:
+        return self._affine
+
+    @property
+    def shape(self):
+        return self._data.shape
+
+    def get_data(self) -> np.ndarray:
+        """Fortran-ordered array; scl_slope/scl_inter applied when valid (nibabel
+        semantics: slope 0 or NaN = no scaling)."""
+        h = self.header
+        slope, inter = float(h["scl_slope"]), float(h["scl_inter"])
+        if np.isfinite(slope) and slope != 0.0 and not (slope == 1.0 and (inter == 0.0 or not np.isfinite(inter))):
+            inter = inter if np.isfinite(inter) else 0.0
+            return self._data * slope + inter
+        return self._data
+
+    get_fdata = get_data
+
+
+def load(path: str) -> Nifti1Image:
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:2] == b"\x1f\x8b":
+        raw = gzip.decompress(raw)
+    if len(raw) < 352:
+        raise ValueError("%s: too small for a NIfTI-1 file" % path)
+    hdr = np.frombuffer(raw[:348], dtype=_HDR)[0].copy()
+    if int(hdr["sizeof_hdr"]) != 348:
+        raise ValueError("%s: not a little-endian NIfTI-1 file (sizeof_hdr=%d)" % (path, int(hdr["sizeof_hdr"])))
+    if bytes(hdr["magic"])[:3] != b"n+1":
+        raise ValueError("%s: only single-file NIfTI-1 (magic n+1) is supported" % path)
+    nd = int(hdr["dim"][0])
+    if not 1 <= nd <= 7:
+        raise ValueError("%s: bad dim[0]=%d" % (path, nd))
+    shape = tuple(int(x) for x in hdr["dim"][1:1 + nd])
+    code = int(hdr["datatype"])
+    if code not in _CODE2DT:
+        raise TypeError("%s: unsupported NIfTI datatype code %d" % (path, code))
+    dt = np.dtype(_CODE2DT[code]).newbyteorder("<")
+    off = int(hdr["vox_offset"]) or 352
+    n = int(np.prod(shape))
+    if len(raw) < off + n * dt.itemsize:
+        raise ValueError("%s: truncated voxel data" % path)
+    data = np.frombuffer(raw, dtype=dt, count=n, offset=off).astype(dt.newbyteorder("=")).reshape(shape, order="F")
+    return Nifti1Image(data, None, hdr)
+
+
+def save(img: Nifti1Image, path: str, compresslevel: int = 1) -> None:
+    img._sync_shape()
+    h = img.header.copy()
+    h["vox_offset"] = 352.0
+    h["magic"] = b"n+1"
+    payload = h.tobytes() + b"\x00\x00\x00\x00" + np.asarray(img._data).astype(
+        np.dtype(img._data.dtype).newbyteorder("<")).tobytes(order="F")
+    tmp = path + ".tmp%d" % os.getpid()
+    if path.endswith(".gz"):
+        with open(tmp, "wb") as f:
+            with gzip.GzipFile(filename="", mode="wb", fileobj=f, compresslevel=compresslevel, mtime=0) as g:
+                g.write(payload)
+    else:
+        with open(tmp, "wb") as f:
+            f.write(payload)
+    os.replace(tmp, path)
