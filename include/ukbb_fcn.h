@@ -124,6 +124,12 @@ int ukbb_fcn_join(ukbb_fcn* h, void* stream);
 /* Block the host until all work of this handle's device has finished. */
 int ukbb_fcn_sync(ukbb_fcn* h);
 
+/* Test hook (BF16 mode): run conv layer `layer` (1..19, graph order) alone on a device BF16 NHWC
+ * tensor in [n][hi][wi][cin] -> out [n][ho][wo][cout] (rows = Y, columns = X), synchronously.
+ * level_out selects the tile shape used for resolution level 0..4. */
+int ukbb_fcn_debug_conv(ukbb_fcn* h, int layer, const void* in_bf16, int n, int hi, int wi, int level_out,
+                        void* out_bf16, void* stream);
+
 /* Introspection used by bench.py: kernels launched by this handle since creation. */
 long long ukbb_fcn_launch_count(const ukbb_fcn* h);
 int ukbb_fcn_mode(const ukbb_fcn* h);

@@ -1,0 +1,113 @@
+"""GPU parity tests, BF16 tensor-core mode (tcgen05 implicit-GEMM convolutions).
+
+Tolerances (BASELINE.json north_star): >= 99.9 % per-pixel label agreement with the
+reference restatement and Dice >= 0.999 per class.  Per-layer unit tests compare every
+tensor-core conv instance with the float64 oracle evaluated on the SAME bf16-rounded inputs
+and weights, so the only differences are FP32 accumulation order and the final bf16
+rounding: |err| <= 2^-7 * |ref| + 2e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import deploy_oracle as do
+from oracle import fcn_oracle as fo
+from ukbb_cardiac_b200 import synth
+from ukbb_cardiac_b200 import weights as W
+from ukbb_cardiac_b200.fcn import FCNEngine
+
+from gpu_util import from_device_labels, from_device_logits, to_device_layout
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16_round(a: np.ndarray) -> np.ndarray:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def layer_reference(w, li, x_dev_layout: np.ndarray) -> np.ndarray:
+    """float64 conv + BN + ReLU of layer li on a device-layout [N, Y, X, C] input."""
+    sp = W.layer_table(4)[li]
+    x_tf = np.transpose(x_dev_layout, (0, 2, 1, 3)).astype(np.float64)             # [N, X, Y, C]
+    k = bf16_round(w[W.conv_name(li) + "/kernel"]).astype(np.float64)
+    y = fo.conv2d_same(torch.from_numpy(np.transpose(x_tf, (0, 3, 1, 2))), k, sp.stride)
+    bn = W.bn_name(li)
+    g, b, m, v = (w[bn + "/" + s].astype(np.float64) for s in ("gamma", "beta", "moving_mean", "moving_variance"))
+    sc = g / np.sqrt(v + 1e-3)
+    y = torch.relu(y * torch.from_numpy(sc).view(1, -1, 1, 1) + torch.from_numpy(b - m * sc).view(1, -1, 1, 1))
+    return np.transpose(y.numpy(), (0, 3, 2, 1))                                    # -> [N, Y, X, C]
+
+
+LAYER_LEVEL = [0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 0, 1, 2, 3, 4, 0, 0]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    w = synth.make_weights(0, 4)
+    eng = FCNEngine(w, mode="bf16")
+    yield eng, w
+    eng.close()
+
+
+@pytest.mark.parametrize("li", list(range(1, 20)))
+def test_tc_layer(engine, li):
+    eng, w = engine
+    sp = W.layer_table(4)[li]
+    lvl = LAYER_LEVEL[li]
+    lvl_in = lvl - 1 if sp.stride == 2 else lvl
+    n, H, Wd = 3, 32 >> lvl_in, 48 >> lvl_in
+    rng = np.random.default_rng(li)
+    x = bf16_round(rng.normal(0.0, 1.0, size=(n, H, Wd, sp.cin)))
+    out = eng.debug_conv(li, torch.from_numpy(x).to(torch.bfloat16).cuda(), lvl).float().cpu().numpy()
+    ref = layer_reference(w, li, x)
+    assert out.shape == ref.shape
+    err = np.abs(out - ref)
+    tol = 2.0 ** -7 * np.abs(ref) + 2e-3
+    assert (err <= tol).all(), "layer %d (%s): max err %g at %s, ref there %g; frac bad %g" % (
+        li, sp.role, err.max(), np.unravel_index(err.argmax(), err.shape), ref.flat[err.argmax()], (err > tol).mean())
+
+
+@pytest.mark.parametrize("n_class", [4, 2, 3, 6])
+def test_forward_bf16_small(n_class):
+    w = synth.make_weights(0, n_class)
+    img = np.random.default_rng(n_class).random((3, 64, 48, 1)).astype(np.float32)
+    with FCNEngine(w, mode="bf16") as eng:
+        labels, logits, _ = eng.forward(to_device_layout(img), want_logits=True)
+        torch.cuda.synchronize()
+    ref = fo.build_fcn(img, w, torch.float64)
+    lg = from_device_logits(logits)
+    rel = np.abs(lg - ref).max() / np.abs(ref).max()
+    assert rel < 0.05, "bf16 logits rel err %g" % rel
+    pred = np.argmax(ref, -1)
+    lab = from_device_labels(labels)
+    agree = (lab == pred).mean()
+    assert agree >= 0.995, agree          # random-noise input: many near-ties; the real criterion is below
+
+
+def test_forward_bf16_sa_label_agreement_and_dice():
+    """north_star BF16 criterion on synthetic SA frames: >= 99.9 % agreement, Dice >= 0.999."""
+    w = synth.make_weights(0, 4)
+    vol = synth.make_stack(0)
+    img = do.rescale_intensity(vol.copy(order="F"), (1, 99))
+    fr = np.concatenate([np.transpose(img[:, :, :, t], (2, 0, 1)) for t in (0, 20)]).astype(np.float32)[..., None]
+    with FCNEngine(w, mode="bf16") as eng:
+        labels, _, _ = eng.forward(to_device_layout(fr))
+        torch.cuda.synchronize()
+    _, pred = fo.session_run(fr, w)
+    lab = from_device_labels(labels)
+    agree = (lab == pred).mean()
+    dice = [fo.categorical_dice(lab, pred, k) for k in range(4)]
+    print("bf16 agreement %.5f dice %s" % (agree, dice))
+    assert agree >= 0.999, agree
+    assert min(dice) >= 0.999, dice
+
+
+def test_segment_volume_bf16_la():
+    w = synth.make_weights(0, 2)
+    vol = synth.make_stack(5, (50, 43, 1, 6))
+    pred_ref, _ = do.deploy_sequence(vol.copy(order="F"), do.make_runner(w))
+    with FCNEngine(w, mode="bf16") as eng:
+        lab, (vl, vh), counts = eng.segment_volume(vol)
+    assert vl == do.percentile_linear(vol, 1) and vh == do.percentile_linear(vol, 99)
+    assert (lab == pred_ref).mean() >= 0.995
+    assert counts.sum() == lab.size

@@ -46,6 +46,8 @@ SIGNATURES = {
     "ukbb_fcn_class_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ukbb_fcn_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ukbb_fcn_sync": (C.c_int, [C.c_void_p]),
+    "ukbb_fcn_debug_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p]),
     "ukbb_fcn_launch_count": (C.c_longlong, [C.c_void_p]),
     "ukbb_fcn_mode": (C.c_int, [C.c_void_p]),
     "ukbb_fcn_n_class": (C.c_int, [C.c_void_p]),

@@ -361,6 +361,15 @@ int ukbb_fcn_sync(ukbb_fcn* hh) {
     return UKBB_OK;
 }
 
+int ukbb_fcn_debug_conv(ukbb_fcn* hh, int layer, const void* in_bf16, int n, int hi, int wi, int level_out,
+                        void* out_bf16, void* stream) {
+    Engine* h = reinterpret_cast<Engine*>(hh);
+    UKBB_REQUIRE(h && in_bf16 && out_bf16, "debug_conv: null argument");
+    UKBB_REQUIRE(h->mode == UKBB_MODE_BF16, "debug_conv: engine is not in BF16 mode");
+    UKBB_CUDA(cudaSetDevice(h->device));
+    return debug_conv_bf16(h, layer, in_bf16, n, hi, wi, level_out, out_bf16, (cudaStream_t)stream);
+}
+
 long long ukbb_fcn_launch_count(const ukbb_fcn* hh) { return hh ? reinterpret_cast<const Engine*>(hh)->launches : 0; }
 int ukbb_fcn_mode(const ukbb_fcn* hh) { return hh ? reinterpret_cast<const Engine*>(hh)->mode : -1; }
 int ukbb_fcn_n_class(const ukbb_fcn* hh) { return hh ? reinterpret_cast<const Engine*>(hh)->n_class : -1; }

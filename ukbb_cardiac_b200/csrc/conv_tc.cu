@@ -1,14 +1,618 @@
-// BF16 tcgen05 path (placeholder until the tensor-core kernels land).
+// BF16 tensor-core path of the FCN forward (north_star (a)-(c)), sm_100a only.
+//
+// conv_tc_kernel: implicit-GEMM convolution (3x3 stride 1/2 or 1x1) + folded BatchNorm + ReLU
+//   (common/network.py:19-25) on tcgen05 tensor cores:
+//     M = 128 output pixels of a (bn x bh x bw) box of the NHWC activation tensor,
+//     N = Cout, K = taps x Cin, accumulated in TMEM (FP32), operands staged by TMA.
+//   For every K block (one filter tap x CC input channels) the producer issues
+//     * one 4-D tiled TMA load of the activation box shifted by the tap offset -- the
+//       out-of-bounds zero fill of TMA IS the TF 'SAME' padding, and the traversal stride of
+//       the tensor map IS the conv stride -- landing as a K-major [128][CC] bf16 tile, and
+//     * one 2-D TMA load of the [Cout][CC] weight slice,
+//   both with the 32/64/128-byte swizzle that the UMMA shared-memory descriptors name.
+//   Warp roles (256 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA
+//   issuer (one elected lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld ->
+//   scale/shift/ReLU -> bf16 -> global NHWC).  Two accumulator stages in TMEM let the epilogue
+//   of tile i overlap the MMAs of tile i+1.
 #include "engine.cuh"
+#include "tc_common.cuh"
+#include <vector>
+#include <string.h>
+
 namespace ukbb {
-int bf16_prepare(Engine*, const ukbb_fcn_weights*) {
-    set_error("BF16 tensor-core mode is not built yet");
+
+using namespace tc;
+
+struct ConvTcParams {
+    int taps, ks, stride, cin;
+    int pad_top, pad_left;
+    int bw, bh, bn;                 // output box of one tile: bw * bh * bn == 128
+    int tiles_x, tiles_y, n_tiles;
+    int ho, wo, n;                  // output height / width / slices actually valid
+    int relu;
+    const float* scale;
+    const float* shift;
+    __nv_bfloat16* out;             // [n][ho][wo][COUT]
+};
+
+template <int CC, int COUT>
+struct ConvTcCfg {
+    static constexpr int A_BYTES = 128 * CC * 2;
+    static constexpr int B_BYTES = COUT * CC * 2;
+    static constexpr int B_PAD = (B_BYTES + 1023) / 1024 * 1024;
+    static constexpr int STAGE_BYTES = A_BYTES + B_PAD;           // both 1024-aligned
+    static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+    static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;   // power of two for COUT in {16..256}
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int CC, int COUT>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const ConvTcParams p) {
+    using Cfg = ConvTcCfg<CC, COUT>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = p.cin / CC;
+    const int kblocks = p.taps * chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, tn = tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * p.bw * p.stride - p.pad_left, y0 = ty * p.bh * p.stride - p.pad_top, n0 = tn * p.bn;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const int tap = kb / chunks, ch = kb - tap * chunks;
+                    const int ky = tap / p.ks, kx = tap - ky * p.ks;
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
+                    tma_load_4d(a_dst, &map_a, full_bar(stage), ch * CC, x0 + kx, y0 + ky, n0);
+                    tma_load_2d(b_dst, &map_b, full_bar(stage), tap * p.cin + ch * CC, 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * COUT;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < CC / 16; ++k) {
+                        const uint64_t ad = make_smem_desc(a_addr + k * 32, CC * 2);
+                        const uint64_t bd = make_smem_desc(b_addr + k * 32, CC * 2);
+                        umma_bf16(d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;                              // TMEM lane quarter of this warp
+        const int r = q * 32 + lane;                         // row of the 128-pixel tile
+        const int rx = r % p.bw, ry = (r / p.bw) % p.bh, rn = r / (p.bw * p.bh);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, tn = tile / (p.tiles_x * p.tiles_y);
+            const int ox = tx * p.bw + rx, oy = ty * p.bh + ry, on = tn * p.bn + rn;
+            const bool live = on < p.n && oy < p.ho && ox < p.wo;
+            __nv_bfloat16* dst = p.out + (((size_t)on * p.ho + oy) * p.wo + ox) * COUT;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * COUT;
+#pragma unroll 1
+            for (int c = 0; c < COUT; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_ld_wait();
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float a = fmaf(__uint_as_float(v[2 * j]), __ldg(p.scale + c + 2 * j), __ldg(p.shift + c + 2 * j));
+                    float b = fmaf(__uint_as_float(v[2 * j + 1]), __ldg(p.scale + c + 2 * j + 1), __ldg(p.shift + c + 2 * j + 1));
+                    if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                    o[j] = pack_bf16(a, b);
+                }
+                if (live) {
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+                    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// conv0_0 (Cin = 1, K = 9): FP32 image in, BF16 NHWC out, CUDA cores (11.5 MFLOP / slice; the
+// kernel is bound by its 1.3 MB / slice output write).  One thread = one pixel x 16 channels.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv0_bf16_kernel(const float* __restrict__ img, const float* __restrict__ wt /*[9][16]*/,
+                  const float* __restrict__ scale, const float* __restrict__ shift,
+                  __nv_bfloat16* __restrict__ out, long long total, int h, int w) {
+    __shared__ float s_w[9 * 16], s_sc[16], s_sh[16];
+    if (threadIdx.x < 144) s_w[threadIdx.x] = wt[threadIdx.x];
+    if (threadIdx.x < 16) { s_sc[threadIdx.x] = scale[threadIdx.x]; s_sh[threadIdx.x] = shift[threadIdx.x]; }
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % w), y = (int)((idx / w) % h);
+    const float* base = img + (idx - (long long)y * w - x);
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int yy = y + ky - 1, xx = x + kx - 1;
+            const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(base + (long long)yy * w + xx) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, s_w[(ky * 3 + kx) * 16 + j], acc[j]);
+        }
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        o[j] = pack_bf16(fmaxf(fmaf(acc[2 * j], s_sc[2 * j], s_sh[2 * j]), 0.f),
+                         fmaxf(fmaf(acc[2 * j + 1], s_sc[2 * j + 1], s_sh[2 * j + 1]), 0.f));
+    uint4* d4 = reinterpret_cast<uint4*>(out + idx * 16);
+    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Bilinear upsample + concat in BF16 (same arithmetic as upsample_concat_fp32_kernel, FP32
+// interpolation, one rounding to BF16).  One thread = one pixel x 8 channels of one level.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample_concat_bf16_kernel(const __nv_bfloat16* __restrict__ s0, const __nv_bfloat16* __restrict__ s1,
+                            const __nv_bfloat16* __restrict__ s2, const __nv_bfloat16* __restrict__ s3,
+                            const __nv_bfloat16* __restrict__ s4, __nv_bfloat16* __restrict__ out, long long total,
+                            int h, int w) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int q = (int)(idx % 20);
+    const long long pix = idx / 20;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h);
+    const long long n = pix / ((long long)w * h);
+    const int l = q / 4, c8 = q % 4;
+    uint4 r;
+    if (l == 0) {
+        r = reinterpret_cast<const uint4*>(s0 + ((n * h + y) * w + x) * 32)[c8];
+    } else {
+        const __nv_bfloat16* src = l == 1 ? s1 : l == 2 ? s2 : l == 3 ? s3 : s4;
+        const int f = 1 << l, pb = (f - 1) / 2;
+        const int hl = h >> l, wl = w >> l;
+        const int ry = (y + pb) % f, y1 = (y + pb) / f, y0 = y1 - 1;
+        const int rx = (x + pb) % f, x1 = (x + pb) / f, x0 = x1 - 1;
+        const float wy1 = (float)(ry + 1) / (float)f, wy0 = 1.f - wy1;
+        const float wx1 = (float)(rx + 1) / (float)f, wx0 = 1.f - wx1;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const __nv_bfloat16* base = src + n * hl * wl * 32;
+        auto tap = [&](int yy, int xx, float wgt) {
+            if (yy < 0 || yy >= hl || xx < 0 || xx >= wl || wgt == 0.f) return;
+            const uint4 v = reinterpret_cast<const uint4*>(base + ((long long)yy * wl + xx) * 32)[c8];
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f2 = __bfloat1622float2(h2[j]);
+                acc[2 * j] = fmaf(f2.x, wgt, acc[2 * j]);
+                acc[2 * j + 1] = fmaf(f2.y, wgt, acc[2 * j + 1]);
+            }
+        };
+        tap(y0, x0, wy0 * wx0); tap(y0, x1, wy0 * wx1); tap(y1, x0, wy1 * wx0); tap(y1, x1, wy1 * wx1);
+        r = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
+                       pack_bf16(acc[6], acc[7]));
+    }
+    reinterpret_cast<uint4*>(out + pix * 160)[q] = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Classifier on BF16 features: 1x1 conv 64 -> n_class (+bias), FP32 softmax, argmax (first
+// maximal index), crop, per-slice class counts.  Same contract as classifier_fp32_kernel.
+// ------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256)
+classifier_bf16_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ wt,
+                       const float* __restrict__ bias, int h2, int w2, int x_pre, int y_pre, int x, int y,
+                       uint8_t* __restrict__ labels, float* __restrict__ logits, float* __restrict__ prob,
+                       unsigned long long* __restrict__ counts) {
+    __shared__ float s_w[64 * NC];
+    __shared__ float s_b[NC];
+    for (int e = threadIdx.x; e < 64 * NC; e += blockDim.x) s_w[e] = wt[e];
+    if (threadIdx.x < NC) s_b[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int n = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < h2 * w2;
+    int label = -1;
+    bool inside = false;
+    if (live) {
+        const uint4* f4 = reinterpret_cast<const uint4*>(feat + ((size_t)n * h2 * w2 + p) * 64);
+        float lg[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) lg[c] = 0.f;
+#pragma unroll 2
+        for (int k8 = 0; k8 < 8; ++k8) {
+            const uint4 v = __ldg(f4 + k8);
+            const __nv_bfloat162* h2p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 f2 = __bfloat1622float2(h2p[u]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    lg[c] = fmaf(f2.x, s_w[(k8 * 8 + 2 * u) * NC + c], lg[c]);
+                    lg[c] = fmaf(f2.y, s_w[(k8 * 8 + 2 * u + 1) * NC + c], lg[c]);
+                }
+            }
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { lg[c] += s_b[c]; m = fmaxf(m, lg[c]); }
+        float e[NC], s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { e[c] = expf(lg[c] - m); s += e[c]; }
+        float best = -1.f;
+        int arg = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float pr = e[c] / s;
+            if (pr > best) { best = pr; arg = c; }
+            if (prob) prob[((size_t)n * h2 * w2 + p) * NC + c] = pr;
+            if (logits) logits[((size_t)n * h2 * w2 + p) * NC + c] = lg[c];
+        }
+        const int yy = p / w2 - y_pre, xx = p % w2 - x_pre;
+        inside = yy >= 0 && yy < y && xx >= 0 && xx < x;
+        if (inside) {
+            labels[((size_t)n * y + yy) * x + xx] = (uint8_t)arg;
+            label = arg;
+        }
+    }
+    if (counts) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const unsigned b = __ballot_sync(0xffffffffu, inside && label == c);
+            if ((threadIdx.x & 31) == 0 && b) atomicAdd(&counts[(size_t)n * NC + c], (unsigned long long)__popc(b));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcLayerPlan {
+    CUtensorMap map_a, map_b;
+    ConvTcParams p;
+    int cc, cout;
+    bool valid = false;
+};
+
+struct Bf16State {
+    EncodeTiledFn encode = nullptr;
+    __nv_bfloat16* w[UKBB_N_CONV] = {};      // [cout][taps*cin] bf16, K-major
+    float* w0 = nullptr;                     // conv0_0 weights [9][16] fp32
+    __nv_bfloat16* cat = nullptr;            // [nb][h][w][160]
+    __nv_bfloat16* f0 = nullptr;             // [nb][h][w][64]
+    __nv_bfloat16* f1 = nullptr;
+    TcLayerPlan plan[UKBB_N_CONV];
+    int plan_nb = 0, plan_h = 0, plan_w = 0;
+};
+
+static CUtensorMapSwizzle swizzle_for(int cc) {
+    return cc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : cc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+static int chunk_for(int cin) { return cin % 64 == 0 ? 64 : cin % 32 == 0 ? 32 : 16; }
+
+static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* out, int nb, int hi, int wi,
+                     int level_out) {
+    Bf16State* S = h->tc;
+    const ConvLayer& L = h->layers[li];
+    TcLayerPlan& P = S->plan[li];
+    const int cc = chunk_for(L.cin);
+    P.cc = cc; P.cout = L.cout;
+    const int s = L.stride, ks = L.ksize;
+    const int ho = (hi + s - 1) / s, wo = (wi + s - 1) / s;
+    int pt = (ho - 1) * s + ks - hi; if (pt < 0) pt = 0; pt /= 2;
+    int pl = (wo - 1) * s + ks - wi; if (pl < 0) pl = 0; pl /= 2;
+    // output box: bw | wo, bh | ho by construction (padded sizes are multiples of 16 at level 0)
+    int bw = 16 >> level_out; if (bw < 1) bw = 1;
+    int bh = 8; while (bh > 1 && (ho % bh != 0 || bw * bh > 128)) bh >>= 1;
+    while (wo % bw != 0 && bw > 1) bw >>= 1;
+    const int bn = 128 / (bw * bh);
+    ConvTcParams& p = P.p;
+    p.taps = ks * ks; p.ks = ks; p.stride = s; p.cin = L.cin; p.pad_top = pt; p.pad_left = pl;
+    p.bw = bw; p.bh = bh; p.bn = bn;
+    p.tiles_x = wo / bw; p.tiles_y = ho / bh;
+    p.ho = ho; p.wo = wo; p.n = nb; p.relu = L.relu; p.scale = L.scale; p.shift = L.shift; p.out = out;
+    p.n_tiles = p.tiles_x * p.tiles_y * ((nb + bn - 1) / bn);
+    // activation map: dims (C, W, H, N), box (cc, bw*s, bh*s, bn), traversal strides (1, s, s, 1)
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)wi, (cuuint64_t)hi, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)wi * L.cin * 2, (cuuint64_t)hi * wi * L.cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)cc, (cuuint32_t)(bw * s), (cuuint32_t)(bh * s), (cuuint32_t)bn};
+        cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+        CUresult r = S->encode(&P.map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)in, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation, layer %d) failed: %d", li, (int)r); return UKBB_E_CUDA; }
+    }
+    {
+        const int ktot = p.taps * L.cin;
+        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)L.cout};
+        cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)cc, (cuuint32_t)L.cout};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = S->encode(&P.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)S->w[li], dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights, layer %d) failed: %d", li, (int)r); return UKBB_E_CUDA; }
+    }
+    P.valid = true;
+    return UKBB_OK;
+}
+
+template <int CC, int COUT>
+static int launch_tc(const TcLayerPlan& P, int sms, cudaStream_t st) {
+    using Cfg = ConvTcCfg<CC, COUT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = P.p.n_tiles < sms ? P.p.n_tiles : sms;
+    conv_tc_kernel<CC, COUT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.p);
+    UKBB_CUDA(cudaGetLastError());
+    return UKBB_OK;
+}
+
+static int launch_plan(const TcLayerPlan& P, int sms, cudaStream_t st) {
+#define CASE(CCV, COUTV) if (P.cc == CCV && P.cout == COUTV) return launch_tc<CCV, COUTV>(P, sms, st)
+    CASE(16, 16); CASE(16, 32);
+    CASE(32, 32); CASE(32, 64);
+    CASE(64, 32); CASE(64, 64); CASE(64, 128); CASE(64, 256);
+#undef CASE
+    set_error("conv_tc: no kernel instance for chunk %d, cout %d", P.cc, P.cout);
     return UKBB_E_UNSUPPORTED;
 }
-void bf16_release(Engine*) {}
-int forward_bf16(Engine*, const float*, int, int, int, int, int, int, int, uint8_t*, float*, float*,
-                 unsigned long long*, cudaStream_t) {
-    set_error("BF16 tensor-core mode is not built yet");
-    return UKBB_E_UNSUPPORTED;
+
+int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
+    Bf16State* S = new Bf16State();
+    h->tc = S;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    UKBB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return UKBB_E_CUDA; }
+    S->encode = (EncodeTiledFn)fn;
+    for (int i = 1; i < UKBB_N_CONV - 1; ++i) {
+        const ukbb_conv_weights& c = w->conv[i];
+        const int taps = c.ksize * c.ksize, ktot = taps * c.cin;
+        std::vector<__nv_bfloat16> wb((size_t)c.cout * ktot);
+        for (int dy = 0; dy < c.ksize; ++dy)
+            for (int dx = 0; dx < c.ksize; ++dx)
+                for (int ci = 0; ci < c.cin; ++ci)
+                    for (int co = 0; co < c.cout; ++co)      // device tap (dy,dx) <- TF kernel[kh=dx][kw=dy]
+                        wb[(size_t)co * ktot + (dy * c.ksize + dx) * c.cin + ci] =
+                            __float2bfloat16(c.kernel[((size_t)(dx * c.ksize + dy) * c.cin + ci) * c.cout + co]);
+        UKBB_CUDA(cudaMalloc(&S->w[i], wb.size() * sizeof(__nv_bfloat16)));
+        UKBB_CUDA(cudaMemcpy(S->w[i], wb.data(), wb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    }
+    return UKBB_OK;
 }
+
+void bf16_release(Engine* h) {
+    Bf16State* S = h->tc;
+    if (!S) return;
+    for (int i = 0; i < UKBB_N_CONV; ++i) cudaFree(S->w[i]);
+    cudaFree(S->w0); cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
+    delete S;
+    h->tc = nullptr;
+}
+
+static const int kNBlockTc[5] = {2, 2, 3, 3, 3};
+static const int kNFilterTc[5] = {16, 32, 64, 128, 256};
+
+static int ensure_plans(Engine* h, int nb, int h2, int w2) {
+    Bf16State* S = h->tc;
+    if (S->plan_nb == nb && S->plan_h == h2 && S->plan_w == w2) return UKBB_OK;
+    UKBB_CUDA(cudaDeviceSynchronize());
+    // activation workspace (bf16): encoder ping/pong + same_dim per level, concat + fc buffers
+    for (int l = 0; l < 5; ++l) {
+        cudaFree(h->ws.a[l]); cudaFree(h->ws.b[l]); cudaFree(h->ws.s[l]);
+        h->ws.a[l] = h->ws.b[l] = h->ws.s[l] = nullptr;
+        const size_t px = (size_t)nb * (h2 >> l) * (w2 >> l);
+        UKBB_CUDA(cudaMalloc(&h->ws.a[l], px * kNFilterTc[l] * 2));
+        UKBB_CUDA(cudaMalloc(&h->ws.b[l], px * kNFilterTc[l] * 2));
+        UKBB_CUDA(cudaMalloc(&h->ws.s[l], px * 32 * 2));
+    }
+    cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
+    S->cat = S->f0 = S->f1 = nullptr;
+    const size_t px = (size_t)nb * h2 * w2;
+    UKBB_CUDA(cudaMalloc(&S->cat, px * 160 * 2));
+    UKBB_CUDA(cudaMalloc(&S->f0, px * 64 * 2));
+    UKBB_CUDA(cudaMalloc(&S->f1, px * 64 * 2));
+    h->ws.nb = nb; h->ws.h = h2; h->ws.w = w2;
+    int li = 0, rc;
+    const __nv_bfloat16* cur = nullptr;
+    const __nv_bfloat16* level_out[5];
+    int hi = h2, wi = w2;
+    for (int l = 0; l < 5; ++l) {
+        for (int b = 0; b < kNBlockTc[l]; ++b, ++li) {
+            __nv_bfloat16* dst = (__nv_bfloat16*)((b & 1) ? h->ws.b[l] : h->ws.a[l]);
+            if (li > 0) {
+                rc = make_plan(h, li, cur, dst, nb, hi, wi, l);
+                if (rc) return rc;
+                hi = S->plan[li].p.ho; wi = S->plan[li].p.wo;
+            }
+            cur = dst;
+        }
+        level_out[l] = cur;
+    }
+    for (int l = 0; l < 5; ++l, ++li) {
+        rc = make_plan(h, li, level_out[l], (__nv_bfloat16*)h->ws.s[l], nb, h2 >> l, w2 >> l, l);
+        if (rc) return rc;
+    }
+    rc = make_plan(h, 18, S->cat, S->f0, nb, h2, w2, 0);
+    if (rc) return rc;
+    rc = make_plan(h, 19, S->f0, S->f1, nb, h2, w2, 0);
+    if (rc) return rc;
+    S->plan_nb = nb; S->plan_h = h2; S->plan_w = w2;
+    return UKBB_OK;
+}
+
+// Test hook: run ONE tensor-core conv layer of the engine on a caller-provided BF16 NHWC tensor.
+int debug_conv_bf16(Engine* h, int li, const void* in, int n, int hi, int wi, int level_out, void* out, cudaStream_t st) {
+    UKBB_REQUIRE(h->tc, "debug_conv: engine is not in BF16 mode");
+    UKBB_REQUIRE(li >= 1 && li < UKBB_N_CONV - 1, "debug_conv: layer %d has no tensor-core kernel", li);
+    Bf16State* S = h->tc;
+    TcLayerPlan saved = S->plan[li];
+    int rc = make_plan(h, li, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, n, hi, wi, level_out);
+    if (!rc) rc = launch_plan(S->plan[li], h->sms, st);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) { set_error("debug_conv: %s", cudaGetErrorString(e)); rc = UKBB_E_CUDA; } }
+    S->plan[li] = saved;
+    h->launches++;
+    return rc;
+}
+
+int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre, int y_pre, int x, int y,
+                 uint8_t* labels, float* logits, float* prob, unsigned long long* counts, cudaStream_t st) {
+    Bf16State* S = h->tc;
+    const int w2 = x2, h2 = y2;
+    UKBB_REQUIRE((w2 >> 4) >= 1 && (h2 >> 4) >= 1, "forward_bf16: image too small");
+    // sub-batch: a multiple of 128 slices would be ideal for the deepest level (bn = 128); keep the
+    // activation working set bounded instead
+    int NB = n < 64 ? n : 64;
+    if (S->plan_nb >= n && S->plan_h == h2 && S->plan_w == w2) NB = S->plan_nb;
+    int rc = ensure_plans(h, NB, h2, w2);
+    if (rc) return rc;
+    for (int n0 = 0; n0 < n; n0 += NB) {
+        const int nb = n - n0 < NB ? n - n0 : NB;
+        {
+            const long long total = (long long)nb * h2 * w2;
+            conv0_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                image + (size_t)n0 * h2 * w2, h->layers[0].w_f32, h->layers[0].scale, h->layers[0].shift,
+                (__nv_bfloat16*)h->ws.a[0], total, h2, w2);
+            UKBB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+        for (int li = 1; li < 18; ++li) {
+            TcLayerPlan P = S->plan[li];
+            P.p.n = nb;
+            P.p.n_tiles = P.p.tiles_x * P.p.tiles_y * ((nb + P.p.bn - 1) / P.p.bn);
+            rc = launch_plan(P, h->sms, st);
+            if (rc) return rc;
+            h->launches++;
+        }
+        {
+            const long long total = (long long)nb * h2 * w2 * 20;
+            upsample_concat_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                (const __nv_bfloat16*)h->ws.s[0], (const __nv_bfloat16*)h->ws.s[1], (const __nv_bfloat16*)h->ws.s[2],
+                (const __nv_bfloat16*)h->ws.s[3], (const __nv_bfloat16*)h->ws.s[4], S->cat, total, h2, w2);
+            UKBB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+        for (int li = 18; li < 20; ++li) {
+            TcLayerPlan P = S->plan[li];
+            P.p.n = nb;
+            P.p.n_tiles = P.p.tiles_x * P.p.tiles_y * ((nb + P.p.bn - 1) / P.p.bn);
+            rc = launch_plan(P, h->sms, st);
+            if (rc) return rc;
+            h->launches++;
+        }
+        {
+            const ConvLayer& L = h->layers[20];
+            dim3 block(256), grid((h2 * w2 + 255) / 256, nb);
+            const size_t po = (size_t)n0 * h2 * w2 * h->n_class;
+            uint8_t* lab = labels + (size_t)n0 * x * y;
+            float* lg = logits ? logits + po : nullptr;
+            float* pr = prob ? prob + po : nullptr;
+            unsigned long long* cn = counts ? counts + (size_t)n0 * h->n_class : nullptr;
+#define LAUNCH(NC) classifier_bf16_kernel<NC><<<grid, block, 0, st>>>(S->f1, L.w_f32, L.shift, h2, w2, x_pre, y_pre, x, y, lab, lg, pr, cn)
+            switch (h->n_class) {
+                case 2: LAUNCH(2); break;
+                case 3: LAUNCH(3); break;
+                case 4: LAUNCH(4); break;
+                case 5: LAUNCH(5); break;
+                case 6: LAUNCH(6); break;
+                case 7: LAUNCH(7); break;
+                case 8: LAUNCH(8); break;
+                default: set_error("classifier: n_class=%d unsupported", h->n_class); return UKBB_E_UNSUPPORTED;
+            }
+#undef LAUNCH
+            UKBB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+    }
+    return UKBB_OK;
+}
+
 }  // namespace ukbb

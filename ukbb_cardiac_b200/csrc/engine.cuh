@@ -43,4 +43,6 @@ void bf16_release(Engine* h);
 int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre, int y_pre, int x, int y,
                  uint8_t* labels, float* logits, float* prob, unsigned long long* counts, cudaStream_t st);
 
+int debug_conv_bf16(Engine* h, int li, const void* in, int n, int hi, int wi, int level_out, void* out, cudaStream_t st);
+
 }  // namespace ukbb

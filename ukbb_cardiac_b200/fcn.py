@@ -224,6 +224,18 @@ class FCNEngine:
                 out.append(logits.permute(0, 2, 1, 3).contiguous().cpu().numpy())
         return out[0] if single else out
 
+    def debug_conv(self, layer: int, x: torch.Tensor, level_out: int) -> torch.Tensor:
+        """Test hook: one tensor-core conv layer on a cuda bfloat16 [N, H, W, Cin] tensor (rows = Y)."""
+        sp = W.layer_table(self.n_class)[layer]
+        assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[3] == sp.cin
+        n, hi, wi, _ = x.shape
+        ho, wo = -(-hi // sp.stride), -(-wi // sp.stride)
+        out = torch.empty((n, ho, wo, sp.cout), dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ukbb_fcn_debug_conv(self._h, layer, x.data_ptr(), n, hi, wi, level_out,
+                                                    out.data_ptr(), self._stream()))
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ukbb_fcn_launch_count(self._h))
