@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("UKBB_BENCH_MODE", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default=os.environ.get("UKBB_BENCH_MODE", "bf16"), choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--subjects", type=int, default=None, help="SA subjects per GPU per step (default 256 bf16, 2 fp32)")
     ap.add_argument("--ref-frames", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=10, help="frames in the cpu_baseline sample (0 = skip)")
@@ -157,7 +157,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    S = args.subjects if args.subjects else (256 if args.mode == "bf16" else 2)
+    S = args.subjects if args.subjects else (2 if args.mode == "fp32" else 256)
     X, Y, Z, T = SA
     nvox = X * Y * Z * T
 
@@ -252,7 +252,7 @@ def main():
             "metric": "SA FCN 192x208 slices/sec", "value": value, "unit": "slices/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": "%d synthetic SA subjects (192x208x10x50, 500 slices each) per GPU per step" % S,
                        "subjects_per_gpu": S, "global_subjects": S * world, "mode": args.mode, "n_class": 4,
                        "l2_policy": "inputs larger than L2: %d distinct 80 MB volumes cycled" % pool,

@@ -56,6 +56,8 @@ extern "C" {
 /* arithmetic modes */
 #define UKBB_MODE_FP32  0   /* FP32 CUDA-core kernels: the exactness mode */
 #define UKBB_MODE_BF16  2   /* BF16 operands, FP32 accumulate on tcgen05 tensor cores */
+#define UKBB_MODE_FP16  3   /* FP16 operands, FP32 accumulate: same kernels and tensor-core rate as
+                               BF16, 11-bit significand (activations are post-BN/ReLU, O(1..100)) */
 
 #define UKBB_N_CONV 21      /* 13 encoder 3x3 + 5 same_dim 1x1 + fc0 + fc1 + logits */
 #define UKBB_MAX_CLASS 8

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libukbb_fcn.so")
 
 MODE_FP32 = 0
 MODE_BF16 = 2
+MODE_FP16 = 3
 N_CONV = 21
 MAX_CLASS = 8
 

@@ -197,7 +197,7 @@ int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode
     *out = nullptr;
     UKBB_REQUIRE(w->n_conv == UKBB_N_CONV && w->conv, "create: expected %d conv layers, got %d", UKBB_N_CONV, w->n_conv);
     UKBB_REQUIRE(n_class >= 2 && n_class <= UKBB_MAX_CLASS, "create: n_class=%d not in [2,%d]", n_class, UKBB_MAX_CLASS);
-    UKBB_REQUIRE(mode == UKBB_MODE_FP32 || mode == UKBB_MODE_BF16, "create: unknown mode %d", mode);
+    UKBB_REQUIRE(mode == UKBB_MODE_FP32 || mode == UKBB_MODE_BF16 || mode == UKBB_MODE_FP16, "create: unknown mode %d", mode);
     for (int i = 0; i < UKBB_N_CONV; ++i) {
         int ks, cin, cout, stride;
         expected_layer(i, n_class, &ks, &cin, &cout, &stride);
@@ -216,8 +216,8 @@ int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode
     UKBB_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     UKBB_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (mode == UKBB_MODE_BF16 && prop.major != 10) {
-        set_error("create: BF16 tensor-core mode needs an sm_100 device, device %d is sm_%d%d", device, prop.major, prop.minor);
+    if (mode != UKBB_MODE_FP32 && prop.major != 10) {
+        set_error("create: tensor-core mode needs an sm_100 device, device %d is sm_%d%d", device, prop.major, prop.minor);
         return UKBB_E_UNSUPPORTED;
     }
     Engine* h = new (std::nothrow) Engine();
@@ -226,7 +226,7 @@ int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode
     int rc = UKBB_OK;
     for (int i = 0; i < UKBB_N_CONV && !rc; ++i) rc = upload_layer(h->layers[i], w->conv[i], w->bn_eps, i == UKBB_N_CONV - 1);
     if (!rc) rc = preproc_alloc(h->pre);
-    if (!rc && mode == UKBB_MODE_BF16) rc = bf16_prepare(h, w);
+    if (!rc && mode != UKBB_MODE_FP32) rc = bf16_prepare(h, w);
     if (!rc) {
         cudaError_t e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
@@ -365,7 +365,7 @@ int ukbb_fcn_debug_conv(ukbb_fcn* hh, int layer, const void* in_bf16, int n, int
                         void* out_bf16, void* stream) {
     Engine* h = reinterpret_cast<Engine*>(hh);
     UKBB_REQUIRE(h && in_bf16 && out_bf16, "debug_conv: null argument");
-    UKBB_REQUIRE(h->mode == UKBB_MODE_BF16, "debug_conv: engine is not in BF16 mode");
+    UKBB_REQUIRE(h->mode != UKBB_MODE_FP32, "debug_conv: engine is not in a tensor-core mode");
     UKBB_CUDA(cudaSetDevice(h->device));
     return debug_conv_bf16(h, layer, in_bf16, n, hi, wi, level_out, out_bf16, (cudaStream_t)stream);
 }

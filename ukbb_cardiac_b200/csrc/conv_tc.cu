@@ -30,6 +30,7 @@ struct ConvTcParams {
     int tiles_x, tiles_y, n_tiles;
     int ho, wo, n;                  // output height / width / slices actually valid
     int relu;
+    int fp16;                       // operand format: 0 = BF16, 1 = FP16
     const float* scale;
     const float* shift;
     __nv_bfloat16* out;             // [n][ho][wo][COUT]
@@ -110,7 +111,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+            const uint32_t idesc = p.fp16 ? make_idesc_f16(128, COUT) : make_idesc_bf16(128, COUT);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -163,7 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     float a = fmaf(__uint_as_float(v[2 * j]), __ldg(p.scale + c + 2 * j), __ldg(p.shift + c + 2 * j));
                     float b = fmaf(__uint_as_float(v[2 * j + 1]), __ldg(p.scale + c + 2 * j + 1), __ldg(p.shift + c + 2 * j + 1));
                     if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                    o[j] = pack_bf16(a, b);
+                    o[j] = pack16(a, b, p.fp16);
                 }
                 if (live) {
                     uint4* d4 = reinterpret_cast<uint4*>(dst + c);
@@ -192,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 __global__ void __launch_bounds__(256)
 conv0_bf16_kernel(const float* __restrict__ img, const float* __restrict__ wt /*[9][16]*/,
                   const float* __restrict__ scale, const float* __restrict__ shift,
-                  __nv_bfloat16* __restrict__ out, long long total, int h, int w) {
+                  __nv_bfloat16* __restrict__ out, long long total, int h, int w, int fp16) {
     __shared__ float s_w[9 * 16], s_sc[16], s_sh[16];
     if (threadIdx.x < 144) s_w[threadIdx.x] = wt[threadIdx.x];
     if (threadIdx.x < 16) { s_sc[threadIdx.x] = scale[threadIdx.x]; s_sh[threadIdx.x] = shift[threadIdx.x]; }
@@ -216,8 +217,8 @@ conv0_bf16_kernel(const float* __restrict__ img, const float* __restrict__ wt /*
     uint32_t o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        o[j] = pack_bf16(fmaxf(fmaf(acc[2 * j], s_sc[2 * j], s_sh[2 * j]), 0.f),
-                         fmaxf(fmaf(acc[2 * j + 1], s_sc[2 * j + 1], s_sh[2 * j + 1]), 0.f));
+        o[j] = pack16(fmaxf(fmaf(acc[2 * j], s_sc[2 * j], s_sh[2 * j]), 0.f),
+                      fmaxf(fmaf(acc[2 * j + 1], s_sc[2 * j + 1], s_sh[2 * j + 1]), 0.f), fp16);
     uint4* d4 = reinterpret_cast<uint4*>(out + idx * 16);
     d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
     d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256)
 upsample_concat_bf16_kernel(const __nv_bfloat16* __restrict__ s0, const __nv_bfloat16* __restrict__ s1,
                             const __nv_bfloat16* __restrict__ s2, const __nv_bfloat16* __restrict__ s3,
                             const __nv_bfloat16* __restrict__ s4, __nv_bfloat16* __restrict__ out, long long total,
-                            int h, int w) {
+                            int h, int w, int fp16) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int q = (int)(idx % 20);
@@ -257,17 +258,17 @@ upsample_concat_bf16_kernel(const __nv_bfloat16* __restrict__ s0, const __nv_bfl
         auto tap = [&](int yy, int xx, float wgt) {
             if (yy < 0 || yy >= hl || xx < 0 || xx >= wl || wgt == 0.f) return;
             const uint4 v = reinterpret_cast<const uint4*>(base + ((long long)yy * wl + xx) * 32)[c8];
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const uint32_t* h2 = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 f2 = __bfloat1622float2(h2[j]);
+                const float2 f2 = unpack16(h2[j], fp16);
                 acc[2 * j] = fmaf(f2.x, wgt, acc[2 * j]);
                 acc[2 * j + 1] = fmaf(f2.y, wgt, acc[2 * j + 1]);
             }
         };
         tap(y0, x0, wy0 * wx0); tap(y0, x1, wy0 * wx1); tap(y1, x0, wy1 * wx0); tap(y1, x1, wy1 * wx1);
-        r = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
-                       pack_bf16(acc[6], acc[7]));
+        r = make_uint4(pack16(acc[0], acc[1], fp16), pack16(acc[2], acc[3], fp16), pack16(acc[4], acc[5], fp16),
+                       pack16(acc[6], acc[7], fp16));
     }
     reinterpret_cast<uint4*>(out + pix * 160)[q] = r;
 }
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256)
 classifier_bf16_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict__ wt,
                        const float* __restrict__ bias, int h2, int w2, int x_pre, int y_pre, int x, int y,
                        uint8_t* __restrict__ labels, float* __restrict__ logits, float* __restrict__ prob,
-                       unsigned long long* __restrict__ counts) {
+                       unsigned long long* __restrict__ counts, int fp16) {
     __shared__ float s_w[64 * NC];
     __shared__ float s_b[NC];
     for (int e = threadIdx.x; e < 64 * NC; e += blockDim.x) s_w[e] = wt[e];
@@ -300,10 +301,10 @@ classifier_bf16_kernel(const __nv_bfloat16* __restrict__ feat, const float* __re
 #pragma unroll 2
         for (int k8 = 0; k8 < 8; ++k8) {
             const uint4 v = __ldg(f4 + k8);
-            const __nv_bfloat162* h2p = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const uint32_t* h2p = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float2 f2 = __bfloat1622float2(h2p[u]);
+                const float2 f2 = unpack16(h2p[u], fp16);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     lg[c] = fmaf(f2.x, s_w[(k8 * 8 + 2 * u) * NC + c], lg[c]);
@@ -365,6 +366,7 @@ struct Bf16State {
     __nv_bfloat16* f1 = nullptr;
     TcLayerPlan plan[UKBB_N_CONV];
     int plan_nb = 0, plan_h = 0, plan_w = 0;
+    int fp16 = 0;
 };
 
 static CUtensorMapSwizzle swizzle_for(int cc) {
@@ -394,6 +396,8 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     p.bw = bw; p.bh = bh; p.bn = bn;
     p.tiles_x = wo / bw; p.tiles_y = ho / bh;
     p.ho = ho; p.wo = wo; p.n = nb; p.relu = L.relu; p.scale = L.scale; p.shift = L.shift; p.out = out;
+    p.fp16 = S->fp16;
+    const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     p.n_tiles = p.tiles_x * p.tiles_y * ((nb + bn - 1) / bn);
     // activation map: dims (C, W, H, N), box (cc, bw*s, bh*s, bn), traversal strides (1, s, s, 1)
     {
@@ -401,7 +405,7 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
         cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)wi * L.cin * 2, (cuuint64_t)hi * wi * L.cin * 2};
         cuuint32_t box[4] = {(cuuint32_t)cc, (cuuint32_t)(bw * s), (cuuint32_t)(bh * s), (cuuint32_t)bn};
         cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
-        CUresult r = S->encode(&P.map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)in, dims, strides, box, estr,
+        CUresult r = S->encode(&P.map_a, dt16, 4, (void*)in, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation, layer %d) failed: %d", li, (int)r); return UKBB_E_CUDA; }
@@ -412,7 +416,7 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
         cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
         cuuint32_t box[2] = {(cuuint32_t)cc, (cuuint32_t)L.cout};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = S->encode(&P.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)S->w[li], dims, strides, box, estr,
+        CUresult r = S->encode(&P.map_b, dt16, 2, (void*)S->w[li], dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights, layer %d) failed: %d", li, (int)r); return UKBB_E_CUDA; }
@@ -453,6 +457,7 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
     UKBB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return UKBB_E_CUDA; }
     S->encode = (EncodeTiledFn)fn;
+    S->fp16 = h->mode == UKBB_MODE_FP16 ? 1 : 0;
     for (int i = 1; i < UKBB_N_CONV - 1; ++i) {
         const ukbb_conv_weights& c = w->conv[i];
         const int taps = c.ksize * c.ksize, ktot = taps * c.cin;
@@ -461,8 +466,12 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
             for (int dx = 0; dx < c.ksize; ++dx)
                 for (int ci = 0; ci < c.cin; ++ci)
                     for (int co = 0; co < c.cout; ++co)      // device tap (dy,dx) <- TF kernel[kh=dx][kw=dy]
-                        wb[(size_t)co * ktot + (dy * c.ksize + dx) * c.cin + ci] =
-                            __float2bfloat16(c.kernel[((size_t)(dx * c.ksize + dy) * c.cin + ci) * c.cout + co]);
+                    {
+                        const float v = c.kernel[((size_t)(dx * c.ksize + dy) * c.cin + ci) * c.cout + co];
+                        __nv_bfloat16& dstw = wb[(size_t)co * ktot + (dy * c.ksize + dx) * c.cin + ci];
+                        if (S->fp16) { const __half hv = __float2half_rn(v); memcpy(&dstw, &hv, 2); }
+                        else dstw = __float2bfloat16(v);
+                    }
         UKBB_CUDA(cudaMalloc(&S->w[i], wb.size() * sizeof(__nv_bfloat16)));
         UKBB_CUDA(cudaMemcpy(S->w[i], wb.data(), wb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     }
@@ -560,7 +569,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             const long long total = (long long)nb * h2 * w2;
             conv0_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
                 image + (size_t)n0 * h2 * w2, h->layers[0].w_f32, h->layers[0].scale, h->layers[0].shift,
-                (__nv_bfloat16*)h->ws.a[0], total, h2, w2);
+                (__nv_bfloat16*)h->ws.a[0], total, h2, w2, S->fp16);
             UKBB_CUDA(cudaGetLastError());
             h->launches++;
         }
@@ -576,7 +585,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             const long long total = (long long)nb * h2 * w2 * 20;
             upsample_concat_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
                 (const __nv_bfloat16*)h->ws.s[0], (const __nv_bfloat16*)h->ws.s[1], (const __nv_bfloat16*)h->ws.s[2],
-                (const __nv_bfloat16*)h->ws.s[3], (const __nv_bfloat16*)h->ws.s[4], S->cat, total, h2, w2);
+                (const __nv_bfloat16*)h->ws.s[3], (const __nv_bfloat16*)h->ws.s[4], S->cat, total, h2, w2, S->fp16);
             UKBB_CUDA(cudaGetLastError());
             h->launches++;
         }
@@ -596,7 +605,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             float* lg = logits ? logits + po : nullptr;
             float* pr = prob ? prob + po : nullptr;
             unsigned long long* cn = counts ? counts + (size_t)n0 * h->n_class : nullptr;
-#define LAUNCH(NC) classifier_bf16_kernel<NC><<<grid, block, 0, st>>>(S->f1, L.w_f32, L.shift, h2, w2, x_pre, y_pre, x, y, lab, lg, pr, cn)
+#define LAUNCH(NC) classifier_bf16_kernel<NC><<<grid, block, 0, st>>>(S->f1, L.w_f32, L.shift, h2, w2, x_pre, y_pre, x, y, lab, lg, pr, cn, S->fp16)
             switch (h->n_class) {
                 case 2: LAUNCH(2); break;
                 case 3: LAUNCH(3); break;

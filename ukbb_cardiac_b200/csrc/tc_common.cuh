@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace ukbb {
@@ -116,6 +117,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// same with FP16 operands (a_format = b_format = 0): identical tensor-core rate, 11-bit significand
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are `row_bytes` wide
 // (32 / 64 / 128 -> SWIZZLE_32B / 64B / 128B, the same mode the TMA tensor map uses): rows are
@@ -131,6 +136,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+// 16-bit operand format of the tensor-core path: 0 = BF16, 1 = FP16 (values clamped to +-65504)
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
+    if (fp16) {
+        __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    return pack_bf16(a, b);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {
+    if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
 }
 
 }  // namespace tc

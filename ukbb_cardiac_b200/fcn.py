@@ -21,7 +21,7 @@ import torch
 from . import _lib, tf_bundle
 from . import weights as W
 
-MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16}
+MODES = {"fp32": _lib.MODE_FP32, "bf16": _lib.MODE_BF16, "fp16": _lib.MODE_FP16}
 
 
 def pad16(x: int) -> Tuple[int, int]:
@@ -227,10 +227,11 @@ class FCNEngine:
     def debug_conv(self, layer: int, x: torch.Tensor, level_out: int) -> torch.Tensor:
         """Test hook: one tensor-core conv layer on a cuda bfloat16 [N, H, W, Cin] tensor (rows = Y)."""
         sp = W.layer_table(self.n_class)[layer]
-        assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[3] == sp.cin
+        dt = torch.float16 if self.mode == "fp16" else torch.bfloat16
+        assert x.is_cuda and x.dtype == dt and x.is_contiguous() and x.shape[3] == sp.cin
         n, hi, wi, _ = x.shape
         ho, wo = -(-hi // sp.stride), -(-wi // sp.stride)
-        out = torch.empty((n, ho, wo, sp.cout), dtype=torch.bfloat16, device=self.device)
+        out = torch.empty((n, ho, wo, sp.cout), dtype=dt, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ukbb_fcn_debug_conv(self._h, layer, x.data_ptr(), n, hi, wi, level_out,
                                                     out.data_ptr(), self._stream()))
