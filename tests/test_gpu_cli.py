@@ -1,0 +1,49 @@
+"""End-to-end drop-in test on the GPU: checkpoint files in the reference's TF layout ->
+common/deploy_network.py CLI -> label NIfTI files, compared with the CPU restatement of the
+reference loop (oracle/deploy_oracle.py) on the same synthetic subjects."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import deploy_oracle as do
+from ukbb_cardiac_b200 import nifti, synth, tf_bundle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("seq,shape,n_class,mode", [("sa", (40, 52, 3, 4), 4, "fp32"), ("la_2ch", (50, 43, 1, 5), 2, "fp32"),
+                                                    ("la_4ch", (50, 43, 1, 5), 3, "fp16")])
+def test_cli_process_seq(tmp_path, seq, shape, n_class, mode):
+    data = tmp_path / "data"
+    w = synth.make_weights(0, n_class)
+    tf_bundle.write_bundle(str(tmp_path / "model" / ("FCN_" + seq)), synth.with_optimizer_slots(w))
+    vols = {}
+    for i in range(2):
+        d = data / ("100000%d" % i)
+        os.makedirs(d)
+        vols[i] = synth.make_stack(10 + i, shape)
+        img = nifti.Nifti1Image(vols[i], np.diag([1.8, 1.8, 10.0, 1.0]))
+        nifti.save(img, str(d / (seq + ".nii.gz")))
+    cmd = [sys.executable, os.path.join(ROOT, "common", "deploy_network.py"), "--seq_name", seq, "--data_dir", str(data),
+           "--model_path", str(tmp_path / "model" / ("FCN_" + seq)), "--mode", mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Start deployment on the data set ..." in r.stdout and "for processing 2 subjects" in r.stdout
+    for i in range(2):
+        d = data / ("100000%d" % i)
+        pred_ref, clipped = do.deploy_sequence(vols[i].copy(order="F"), do.make_runner(w))
+        seg = nifti.load(str(d / ("seg_%s.nii.gz" % seq))).get_data()
+        assert seg.dtype == np.float64 and seg.shape == shape
+        agree = (seg == pred_ref).mean()
+        assert agree >= (1 - 2e-5 if mode == "fp32" else 0.996), agree
+        es = do.es_frame(seg, seq)
+        assert "ED frame = 0, ES frame = %d" % es in r.stdout
+        np.testing.assert_array_equal(nifti.load(str(d / ("seg_%s_ES.nii.gz" % seq))).get_data(), seg[:, :, :, es])
+        np.testing.assert_array_equal(nifti.load(str(d / ("%s_ED.nii.gz" % seq))).get_data(), clipped[:, :, :, 0])
+    # second run: everything is skipped (resume rule)
+    r2 = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0 and "for processing 0 subjects" in r2.stdout
