@@ -16,6 +16,8 @@
 //   of tile i overlap the MMAs of tile i+1.
 #include "engine.cuh"
 #include "tc_common.cuh"
+#include "conv_halo.cuh"
+#include <stdlib.h>
 #include <vector>
 #include <string.h>
 
@@ -353,7 +355,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct TcLayerPlan {
     CUtensorMap map_a, map_b;
     ConvTcParams p;
+    ConvHaloParams hp;
     int cc, cout;
+    int kind = 0;                   // 0 = per-tap implicit GEMM (conv_tc_kernel), 1 = halo reuse (conv_halo_kernel)
     bool valid = false;
 };
 
@@ -399,6 +403,21 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     p.fp16 = S->fp16;
     const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     p.n_tiles = p.tiles_x * p.tiles_y * ((nb + bn - 1) / bn);
+    P.kind = (ks == 3 && s == 1 && L.cin >= 16 && !getenv("UKBB_NO_HALO")) ? 1 : 0;
+    if (P.kind == 1) {
+        ConvHaloParams& hp = P.hp;
+        hp.cin = L.cin; hp.chunks = L.cin / cc;
+        hp.tiles_x = (wo + 15) / 16; hp.tiles_y = (ho + 15) / 16; hp.n_tiles = hp.tiles_x * hp.tiles_y * nb;
+        hp.ho = ho; hp.wo = wo; hp.n = nb; hp.relu = L.relu; hp.fp16 = S->fp16;
+        hp.scale = L.scale; hp.shift = L.shift; hp.out = out;
+        cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)wi, (cuuint64_t)hi, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {(cuuint64_t)L.cin * 2, (cuuint64_t)wi * L.cin * 2, (cuuint64_t)hi * wi * L.cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)cc, 18, 18, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = S->encode(&P.map_a, dt16, 4, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               swizzle_for(cc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(halo patch, layer %d) failed: %d", li, (int)r); return UKBB_E_CUDA; }
+    } else
     // activation map: dims (C, W, H, N), box (cc, bw*s, bh*s, bn), traversal strides (1, s, s, 1)
     {
         cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)wi, (cuuint64_t)hi, (cuuint64_t)nb};
@@ -439,7 +458,31 @@ static int launch_tc(const TcLayerPlan& P, int sms, cudaStream_t st) {
     return UKBB_OK;
 }
 
+template <int CC, int COUT, bool RESIDENT, int NKB>
+static int launch_halo(const TcLayerPlan& P, int sms, cudaStream_t st) {
+    using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, RESIDENT, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = P.hp.n_tiles < sms ? P.hp.n_tiles : sms;
+    conv_halo_kernel<CC, COUT, RESIDENT, NKB><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.hp);
+    UKBB_CUDA(cudaGetLastError());
+    return UKBB_OK;
+}
+
 static int launch_plan(const TcLayerPlan& P, int sms, cudaStream_t st) {
+    if (P.kind == 1) {
+        if (P.cc == 16 && P.cout == 16 && P.hp.chunks == 1) return launch_halo<16, 16, true, 9>(P, sms, st);
+        if (P.cc == 32 && P.cout == 32 && P.hp.chunks == 1) return launch_halo<32, 32, true, 9>(P, sms, st);
+        if (P.cc == 64 && P.cout == 64 && P.hp.chunks == 1) return launch_halo<64, 64, true, 9>(P, sms, st);
+        if (P.cc == 64 && P.cout == 128) return launch_halo<64, 128, false, 0>(P, sms, st);
+        if (P.cc == 64 && P.cout == 256) return launch_halo<64, 256, false, 0>(P, sms, st);
+        set_error("conv_halo: no kernel instance for chunk %d x %d, cout %d", P.cc, P.hp.chunks, P.cout);
+        return UKBB_E_UNSUPPORTED;
+    }
 #define CASE(CCV, COUTV) if (P.cc == CCV && P.cout == COUTV) return launch_tc<CCV, COUTV>(P, sms, st)
     CASE(16, 16); CASE(16, 32);
     CASE(32, 32); CASE(32, 64);
@@ -577,6 +620,8 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             TcLayerPlan P = S->plan[li];
             P.p.n = nb;
             P.p.n_tiles = P.p.tiles_x * P.p.tiles_y * ((nb + P.p.bn - 1) / P.p.bn);
+            P.hp.n = nb;
+            P.hp.n_tiles = P.hp.tiles_x * P.hp.tiles_y * nb;
             rc = launch_plan(P, h->sms, st);
             if (rc) return rc;
             h->launches++;
