@@ -125,3 +125,23 @@ def test_segment_volume_tc_la(mode):
     assert vl == do.percentile_linear(vol, 1) and vh == do.percentile_linear(vol, 99)
     assert (lab == pred_ref).mean() >= (0.98 if mode == "bf16" else 0.997)
     assert counts.sum() == lab.size
+
+
+def test_fused_and_unfused_paths_agree(monkeypatch):
+    """The fused head / halo-reuse kernels and the stage-1 kernels (per-tap TMA, materialised
+    concat) implement the same arithmetic: labels agree except at near-ties, logits within the
+    16-bit rounding of the two extra intermediate tensors of the unfused path."""
+    w = synth.make_weights(0, 4)
+    img = np.random.default_rng(11).random((2, 64, 96, 1)).astype(np.float32)
+    dev = to_device_layout(img)
+    with FCNEngine(w, mode="fp16") as eng:
+        l1, g1, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+    monkeypatch.setenv("UKBB_NO_FUSED_HEAD", "1")
+    monkeypatch.setenv("UKBB_NO_HALO", "1")
+    with FCNEngine(w, mode="fp16") as eng:
+        l2, g2, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+    rel = float((g1 - g2).abs().max() / g2.abs().max())
+    assert rel < 5e-3, rel
+    assert float((l1 == l2).float().mean()) >= 0.998

@@ -17,6 +17,7 @@
 #include "engine.cuh"
 #include "tc_common.cuh"
 #include "conv_halo.cuh"
+#include "head_fused.cuh"
 #include <stdlib.h>
 #include <vector>
 #include <string.h>
@@ -371,6 +372,8 @@ struct Bf16State {
     TcLayerPlan plan[UKBB_N_CONV];
     int plan_nb = 0, plan_h = 0, plan_w = 0;
     int fp16 = 0;
+    int fused_head = 1;
+    CUtensorMap map_s0, map_w0, map_w1;      // fused head operands
 };
 
 static CUtensorMapSwizzle swizzle_for(int cc) {
@@ -501,6 +504,7 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
     if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return UKBB_E_CUDA; }
     S->encode = (EncodeTiledFn)fn;
     S->fp16 = h->mode == UKBB_MODE_FP16 ? 1 : 0;
+    S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : 1;
     for (int i = 1; i < UKBB_N_CONV - 1; ++i) {
         const ukbb_conv_weights& c = w->conv[i];
         const int taps = c.ksize * c.ksize, ktot = taps * c.cin;
@@ -577,7 +581,38 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
     if (rc) return rc;
     rc = make_plan(h, 19, S->f0, S->f1, nb, h2, w2, 0);
     if (rc) return rc;
+    {   // fused head operands: s0 tiles (8 rows x 16 columns x 32 channels), fc0 / fc1 weights
+        const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        cuuint64_t dims[4] = {32, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {64, (cuuint64_t)w2 * 64, (cuuint64_t)h2 * w2 * 64};
+        cuuint32_t box[4] = {32, 16, 8, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = S->encode(&S->map_s0, dt16, 4, h->ws.s[0], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        cuuint64_t d0[2] = {160, 64}; cuuint64_t st0[1] = {320}; cuuint32_t b0[2] = {32, 64}; cuuint32_t e2[2] = {1, 1};
+        if (r == CUDA_SUCCESS)
+            r = S->encode(&S->map_w0, dt16, 2, S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        cuuint64_t d1[2] = {64, 64}; cuuint64_t st1[1] = {128}; cuuint32_t b1[2] = {64, 64};
+        if (r == CUDA_SUCCESS)
+            r = S->encode(&S->map_w1, dt16, 2, S->w[19], d1, st1, b1, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(fused head) failed: %d", (int)r); return UKBB_E_CUDA; }
+    }
     S->plan_nb = nb; S->plan_h = h2; S->plan_w = w2;
+    return UKBB_OK;
+}
+
+template <int NC>
+static int launch_head(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(head_fused_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM));
+        attr_set = true;
+    }
+    const int grid = hp.n_tiles < sms ? hp.n_tiles : sms;
+    head_fused_kernel<NC><<<grid, HEAD_THREADS, HEAD_SMEM, st>>>(S->map_s0, S->map_w0, S->map_w1, hp);
+    UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
 }
 
@@ -625,6 +660,32 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             rc = launch_plan(P, h->sms, st);
             if (rc) return rc;
             h->launches++;
+        }
+        if (S->fused_head) {
+            HeadParams hp;
+            for (int l = 0; l < 5; ++l) hp.s[l] = (const __nv_bfloat16*)h->ws.s[l];
+            hp.n = nb; hp.h = h2; hp.w = w2;
+            hp.tiles_x = w2 / 16; hp.tiles_y = h2 / 8; hp.n_tiles = hp.tiles_x * hp.tiles_y * nb;
+            hp.x_pre = x_pre; hp.y_pre = y_pre; hp.x = x; hp.y = y;
+            hp.fp16 = S->fp16; hp.nc = h->n_class;
+            hp.scale0 = h->layers[18].scale; hp.shift0 = h->layers[18].shift;
+            hp.scale1 = h->layers[19].scale; hp.shift1 = h->layers[19].shift;
+            hp.wlog = h->layers[20].w_f32; hp.blog = h->layers[20].shift;
+            const size_t po = (size_t)n0 * h2 * w2 * h->n_class;
+            hp.labels = labels + (size_t)n0 * x * y;
+            hp.logits = logits ? logits + po : nullptr;
+            hp.prob = prob ? prob + po : nullptr;
+            hp.counts = counts ? counts + (size_t)n0 * h->n_class : nullptr;
+            switch (h->n_class) {
+                case 2: rc = launch_head<2>(S, hp, h->sms, st); break;
+                case 3: rc = launch_head<3>(S, hp, h->sms, st); break;
+                case 4: rc = launch_head<4>(S, hp, h->sms, st); break;
+                case 5: case 6: rc = launch_head<6>(S, hp, h->sms, st); break;
+                default: rc = launch_head<8>(S, hp, h->sms, st); break;
+            }
+            if (rc) return rc;
+            h->launches++;
+            continue;
         }
         {
             const long long total = (long long)nb * h2 * w2 * 20;
