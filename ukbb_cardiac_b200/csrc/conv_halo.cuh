@@ -46,7 +46,7 @@ struct ConvHaloCfg {
     static_assert(A_STAGES >= 2, "need at least two patch stages");
 };
 
-template <int CC, int COUT, bool RESIDENT, int NKB>
+template <int CC, int COUT, bool RESIDENT, int NKB, bool F16>
 __global__ void __launch_bounds__(256, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const ConvHaloParams p) {
@@ -125,53 +125,65 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = p.fp16 ? make_idesc_f16(128, COUT) : make_idesc_bf16(128, COUT);
-            constexpr uint64_t SBO_MASK = ~(0x3FFFull << 32);
-            constexpr uint64_t SBO_PATCH = (uint64_t)((18 * RB) >> 4) << 32;
-            if (RESIDENT) { mbar_wait(wfull, 0); tc_fence_after(); }
-            int as = 0, bs = 0, acc = 0;
-            uint32_t aph = 0, bph = 0, acc_ph = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                mbar_wait(tempty(acc), acc_ph ^ 1);
+        // The whole warp runs the control flow (uniform registers, no divergence); one elected lane
+        // issues the tcgen05.mma / tcgen05.commit instructions.  Descriptors are (lo, hi) pairs: hi is
+        // constant per operand kind, lo = base + compile-time offset of the (tap, sub-tile, k) window.
+        const bool leader = elect_one();
+        const uint32_t idesc = F16 ? make_idesc_f16(128, COUT) : make_idesc_bf16(128, COUT);
+        const uint32_t layout = RB == 128 ? 2u : RB == 64 ? 4u : 6u;
+        const uint32_t a_hi = (uint32_t)((18 * RB) >> 4) | (1u << 14) | (layout << 29);     // SBO = 18 patch rows
+        const uint32_t b_hi = (uint32_t)((8 * RB) >> 4) | (1u << 14) | (layout << 29);      // SBO = 8 rows
+        if (RESIDENT) { mbar_wait(wfull, 0); tc_fence_after(); }
+        int as = 0, bs = 0, acc = 0;
+        uint32_t aph = 0, bph = 0, acc_ph = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(tempty(acc), acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + acc * (2 * COUT);
+            for (int ch = 0; ch < p.chunks; ++ch) {
+                mbar_wait(a_full(as), aph);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + acc * (2 * COUT);
-                for (int ch = 0; ch < p.chunks; ++ch) {
-                    mbar_wait(a_full(as), aph);
-                    tc_fence_after();
-                    const uint32_t patch = smem_base + as * Cfg::PATCH_BYTES;
+                const uint32_t a_lo = (((smem_base + as * Cfg::PATCH_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+                if (RESIDENT) {
+                    const uint32_t b_lo = (((b_base + ch * 9 * Cfg::B_TILE) & 0x3FFFF) >> 4) | (1u << 16);
+                    if (leader) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                for (int k = 0; k < CC / 16; ++k)
+                                    umma_bf16_lohi(d0 + h * COUT, a_lo + ((((tap / 3) * 18 + (tap % 3) + 8 * h) * RB + k * 32) >> 4), a_hi,
+                                                   b_lo + ((tap * Cfg::B_TILE + k * 32) >> 4), b_hi, idesc,
+                                                   (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+                    }
+                } else {
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        uint32_t b_addr;
-                        if (RESIDENT) {
-                            b_addr = b_base + (ch * 9 + tap) * Cfg::B_TILE;
-                        } else {
-                            mbar_wait(b_full(bs), bph);
-                            tc_fence_after();
-                            b_addr = b_base + bs * Cfg::B_TILE;
-                        }
-                        const int ky = tap / 3, kx = tap - ky * 3;
-                        const uint32_t win = patch + (ky * 18 + kx) * RB;
+                        mbar_wait(b_full(bs), bph);
+                        tc_fence_after();
+                        const uint32_t b_lo = (((b_base + bs * Cfg::B_TILE) & 0x3FFFF) >> 4) | (1u << 16);
+                        const uint32_t w_lo = a_lo + ((((tap / 3) * 18 + (tap % 3)) * RB) >> 4);
+                        if (leader) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
+                            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                            for (int k = 0; k < CC / 16; ++k) {
-                                const uint64_t ad = (make_smem_desc(win + h * 8 * RB + k * 32, RB) & SBO_MASK) | SBO_PATCH;
-                                const uint64_t bd = make_smem_desc(b_addr + k * 32, RB);
-                                umma_bf16(d0 + h * COUT, ad, bd, idesc, (ch | tap | k) != 0 ? 1u : 0u);
-                            }
-                        }
-                        if (!RESIDENT) {
+                                for (int k = 0; k < CC / 16; ++k)
+                                    umma_bf16_lohi(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi,
+                                                   idesc, (ch | tap | k) != 0 ? 1u : 0u);
                             umma_commit(b_empty(bs));
-                            if (++bs == BST) { bs = 0; bph ^= 1; }
                         }
+                        __syncwarp();
+                        if (++bs == BST) { bs = 0; bph ^= 1; }
                     }
-                    umma_commit(a_empty(as));
-                    if (++as == AST) { as = 0; aph ^= 1; }
                 }
-                umma_commit(tfull(acc));
-                if (++acc == ACC) { acc = 0; acc_ph ^= 1; }
+                if (leader) umma_commit(a_empty(as));
+                __syncwarp();
+                if (++as == AST) { as = 0; aph ^= 1; }
             }
+            if (leader) umma_commit(tfull(acc));
+            __syncwarp();
+            if (++acc == ACC) { acc = 0; acc_ph ^= 1; }
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -198,11 +210,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tmem_ld_wait();
                     uint32_t o[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float a = fmaf(__uint_as_float(v[2 * j]), s_scale[c + 2 * j], s_shift[c + 2 * j]);
-                        float b = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c + 2 * j + 1], s_shift[c + 2 * j + 1]);
-                        if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                        o[j] = pack16(a, b, p.fp16);
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + 4 * j4);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + 4 * j4);
+                        float a0 = fmaf(__uint_as_float(v[4 * j4]), sc.x, sh.x), a1 = fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y);
+                        float a2 = fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z), a3 = fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w);
+                        if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                        else if (F16) { a0 = fmaxf(a0, -65504.f); a1 = fmaxf(a1, -65504.f); a2 = fmaxf(a2, -65504.f); a3 = fmaxf(a3, -65504.f); }
+                        o[2 * j4] = pack16t<F16>(a0, a1);
+                        o[2 * j4 + 1] = pack16t<F16>(a2, a3);
                     }
                     if (live) {
                         uint4* d4 = reinterpret_cast<uint4*>(dst + c);

@@ -51,7 +51,7 @@ struct ConvTcCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int CC, int COUT>
+template <int CC, int COUT, bool F16>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcParams p) {
@@ -112,34 +112,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = p.fp16 ? make_idesc_f16(128, COUT) : make_idesc_bf16(128, COUT);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+        const bool leader = elect_one();
+        const uint32_t idesc = F16 ? make_idesc_f16(128, COUT) : make_idesc_bf16(128, COUT);
+        constexpr uint32_t RB = CC * 2;
+        constexpr uint32_t HI = (uint32_t)((8 * RB) >> 4) | (1u << 14) | ((RB == 128 ? 2u : RB == 64 ? 4u : 6u) << 29);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + acc * COUT;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t d = tmem_base + acc * COUT;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                const uint32_t a_lo = (((smem_base + stage * Cfg::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+                const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
+                if (leader) {
 #pragma unroll
-                    for (int k = 0; k < CC / 16; ++k) {
-                        const uint64_t ad = make_smem_desc(a_addr + k * 32, CC * 2);
-                        const uint64_t bd = make_smem_desc(b_addr + k * 32, CC * 2);
-                        umma_bf16(d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < CC / 16; ++k)
+                        umma_bf16_lohi(d, a_lo + 2 * k, HI, b_lo + 2 * k, HI, idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == kblocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
                 }
-                umma_commit(tfull_bar(acc));                // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -163,11 +164,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld_wait();
                 uint32_t o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float a = fmaf(__uint_as_float(v[2 * j]), __ldg(p.scale + c + 2 * j), __ldg(p.shift + c + 2 * j));
-                    float b = fmaf(__uint_as_float(v[2 * j + 1]), __ldg(p.scale + c + 2 * j + 1), __ldg(p.shift + c + 2 * j + 1));
-                    if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                    o[j] = pack16(a, b, p.fp16);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c) + j4);
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c) + j4);
+                    float a0 = fmaf(__uint_as_float(v[4 * j4]), sc.x, sh.x), a1 = fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y);
+                    float a2 = fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z), a3 = fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w);
+                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                    else if (F16) { a0 = fmaxf(a0, -65504.f); a1 = fmaxf(a1, -65504.f); a2 = fmaxf(a2, -65504.f); a3 = fmaxf(a3, -65504.f); }
+                    o[2 * j4] = pack16t<F16>(a0, a1);
+                    o[2 * j4 + 1] = pack16t<F16>(a2, a3);
                 }
                 if (live) {
                     uint4* d4 = reinterpret_cast<uint4*>(dst + c);
@@ -447,33 +452,41 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     return UKBB_OK;
 }
 
-template <int CC, int COUT>
-static int launch_tc(const TcLayerPlan& P, int sms, cudaStream_t st) {
+template <int CC, int COUT, bool F16>
+static int launch_tc2(const TcLayerPlan& P, int sms, cudaStream_t st) {
     using Cfg = ConvTcCfg<CC, COUT>;
     static bool attr_set = false;
     if (!attr_set) {
-        UKBB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CC, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        UKBB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CC, COUT, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = P.p.n_tiles < sms ? P.p.n_tiles : sms;
-    conv_tc_kernel<CC, COUT><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.p);
+    conv_tc_kernel<CC, COUT, F16><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.p);
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
 }
+template <int CC, int COUT>
+static int launch_tc(const TcLayerPlan& P, int sms, cudaStream_t st) {
+    return P.p.fp16 ? launch_tc2<CC, COUT, true>(P, sms, st) : launch_tc2<CC, COUT, false>(P, sms, st);
+}
 
-template <int CC, int COUT, bool RESIDENT, int NKB>
-static int launch_halo(const TcLayerPlan& P, int sms, cudaStream_t st) {
+template <int CC, int COUT, bool RESIDENT, int NKB, bool F16>
+static int launch_halo2(const TcLayerPlan& P, int sms, cudaStream_t st) {
     using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB>;
     static bool attr_set = false;
     if (!attr_set) {
-        UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, RESIDENT, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, RESIDENT, NKB, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = P.hp.n_tiles < sms ? P.hp.n_tiles : sms;
-    conv_halo_kernel<CC, COUT, RESIDENT, NKB><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.hp);
+    conv_halo_kernel<CC, COUT, RESIDENT, NKB, F16><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.hp);
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
+}
+template <int CC, int COUT, bool RESIDENT, int NKB>
+static int launch_halo(const TcLayerPlan& P, int sms, cudaStream_t st) {
+    return P.hp.fp16 ? launch_halo2<CC, COUT, RESIDENT, NKB, true>(P, sms, st) : launch_halo2<CC, COUT, RESIDENT, NKB, false>(P, sms, st);
 }
 
 static int launch_plan(const TcLayerPlan& P, int sms, cudaStream_t st) {
@@ -603,17 +616,21 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
     return UKBB_OK;
 }
 
-template <int NC>
-static int launch_head(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+template <int NC, bool F16>
+static int launch_head2(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        UKBB_CUDA(cudaFuncSetAttribute(head_fused_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM));
+        UKBB_CUDA(cudaFuncSetAttribute(head_fused_kernel<NC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM));
         attr_set = true;
     }
     const int grid = hp.n_tiles < sms ? hp.n_tiles : sms;
-    head_fused_kernel<NC><<<grid, HEAD_THREADS, HEAD_SMEM, st>>>(S->map_s0, S->map_w0, S->map_w1, hp);
+    head_fused_kernel<NC, F16><<<grid, HEAD_THREADS, HEAD_SMEM, st>>>(S->map_s0, S->map_w0, S->map_w1, hp);
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
+}
+template <int NC>
+static int launch_head(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+    return S->fp16 ? launch_head2<NC, true>(S, hp, sms, st) : launch_head2<NC, false>(S, hp, sms, st);
 }
 
 // Test hook: run ONE tensor-core conv layer of the engine on a caller-provided BF16 NHWC tensor.
@@ -637,7 +654,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
     UKBB_REQUIRE((w2 >> 4) >= 1 && (h2 >> 4) >= 1, "forward_bf16: image too small");
     // sub-batch: a multiple of 128 slices would be ideal for the deepest level (bn = 128); keep the
     // activation working set bounded instead
-    int NB = n < 64 ? n : 64;
+    int NB = n < 128 ? n : 128;
     if (S->plan_nb >= n && S->plan_h == h2 && S->plan_w == w2) NB = S->plan_nb;
     int rc = ensure_plans(h, NB, h2, w2);
     if (rc) return rc;

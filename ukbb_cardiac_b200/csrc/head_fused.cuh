@@ -47,7 +47,7 @@ constexpr int HEAD_W1_BYTES = 64 * 128;         // fc1: [64 rows][128 B]
 constexpr int HEAD_SMEM = 2 * HEAD_A_BYTES + 2 * HEAD_A2_BYTES + HEAD_W0_BYTES + HEAD_W1_BYTES + 1024 /*align*/ +
                           256 /*barriers*/ + (4 * 64 + 64 * 8 + 8) * 4 /*scale/shift, wlog, blog*/;
 
-template <int NC>
+template <int NC, bool F16>
 __global__ void __launch_bounds__(HEAD_THREADS, 1)
 head_fused_kernel(const __grid_constant__ CUtensorMap map_s0, const __grid_constant__ CUtensorMap map_w0,
                   const __grid_constant__ CUtensorMap map_w1, const HeadParams p) {
@@ -116,47 +116,57 @@ head_fused_kernel(const __grid_constant__ CUtensorMap map_s0, const __grid_const
             }
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = p.fp16 ? make_idesc_f16(128, 64) : make_idesc_bf16(128, 64);
-            mbar_wait(BAR(0), 0);
+        // ===================== MMA issuer (whole warp runs the control flow, one elected lane issues) ============
+        const bool leader = elect_one();
+        const uint32_t idesc = F16 ? make_idesc_f16(128, 64) : make_idesc_bf16(128, 64);
+        constexpr uint32_t HI64 = (uint32_t)((8 * 64) >> 4) | (1u << 14) | (4u << 29);      // SWIZZLE_64B, SBO = 8 rows
+        constexpr uint32_t HI128 = (uint32_t)((8 * 128) >> 4) | (1u << 14) | (2u << 29);    // SWIZZLE_128B
+        const uint32_t w0_lo = ((w0_base & 0x3FFFF) >> 4) | (1u << 16);
+        const uint32_t w1_lo = ((w1_base & 0x3FFFF) >> 4) | (1u << 16);
+        mbar_wait(BAR(0), 0);
+        tc_fence_after();
+        auto issue1 = [&](int i) {
+            const int b = i & 1;
+            const uint32_t ph = (i >> 1) & 1;
+            mbar_wait(BAR(1 + b), ph);
+            mbar_wait(BAR(3 + b), ph);
+            mbar_wait(BAR(9 + b), ph ^ 1);
             tc_fence_after();
-            auto issue1 = [&](int i) {
-                const int b = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
-                mbar_wait(BAR(1 + b), ph);
-                mbar_wait(BAR(3 + b), ph);
-                mbar_wait(BAR(9 + b), ph ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + b * 64;
+            const uint32_t d = tmem_base + b * 64;
+            const uint32_t a_lo = (((a_base + b * HEAD_A_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+            if (leader) {
 #pragma unroll
                 for (int c = 0; c < 5; ++c)
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
-                        umma_bf16(d, make_smem_desc(a_base + b * HEAD_A_BYTES + c * 8192 + k * 32, 64),
-                                  make_smem_desc(w0_base + c * 4096 + k * 32, 64), idesc, (c | k) != 0 ? 1u : 0u);
+                        umma_bf16_lohi(d, a_lo + ((c * 8192 + k * 32) >> 4), HI64, w0_lo + ((c * 4096 + k * 32) >> 4), HI64, idesc,
+                                       (c | k) != 0 ? 1u : 0u);
                 umma_commit(BAR(5 + b));
                 umma_commit(BAR(7 + b));
-            };
-            auto issue2 = [&](int i) {
-                const int b = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
-                mbar_wait(BAR(11 + b), ph);
-                mbar_wait(BAR(17 + b), ph ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + 128 + b * 64;
+            }
+            __syncwarp();
+        };
+        auto issue2 = [&](int i) {
+            const int b = i & 1;
+            const uint32_t ph = (i >> 1) & 1;
+            mbar_wait(BAR(11 + b), ph);
+            mbar_wait(BAR(17 + b), ph ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + 128 + b * 64;
+            const uint32_t a_lo = (((a2_base + b * HEAD_A2_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+            if (leader) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_bf16(d, make_smem_desc(a2_base + b * HEAD_A2_BYTES + k * 32, 128),
-                              make_smem_desc(w1_base + k * 32, 128), idesc, k != 0 ? 1u : 0u);
+                    umma_bf16_lohi(d, a_lo + ((k * 32) >> 4), HI128, w1_lo + ((k * 32) >> 4), HI128, idesc, k != 0 ? 1u : 0u);
                 umma_commit(BAR(13 + b));
                 umma_commit(BAR(15 + b));
-            };
-            if (my_tiles > 0) issue1(0);
-            for (int i = 0; i < my_tiles; ++i) {
-                if (i + 1 < my_tiles) issue1(i + 1);
-                issue2(i);
             }
+            __syncwarp();
+        };
+        if (my_tiles > 0) issue1(0);
+        for (int i = 0; i < my_tiles; ++i) {
+            if (i + 1 < my_tiles) issue1(i + 1);
+            issue2(i);
         }
     } else if (warp >= 6) {
         // ===================== bilinear gather (levels 1-4 -> A chunks 1-4) =====================
@@ -194,7 +204,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap map_s0, const __grid_const
                         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 f2 = unpack16(u[j], p.fp16);
+                            const float2 f2 = unpack16t<F16>(u[j]);
                             acc[q4 * 8 + 2 * j] = fmaf(f2.x, wgt, acc[q4 * 8 + 2 * j]);
                             acc[q4 * 8 + 2 * j + 1] = fmaf(f2.y, wgt, acc[q4 * 8 + 2 * j + 1]);
                         }
@@ -207,8 +217,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap map_s0, const __grid_const
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t dst = row + (((uint32_t)j ^ ((uint32_t)(m >> 1) & 3u)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                                 "r"(pack16(acc[8 * j], acc[8 * j + 1], p.fp16)), "r"(pack16(acc[8 * j + 2], acc[8 * j + 3], p.fp16)),
-                                 "r"(pack16(acc[8 * j + 4], acc[8 * j + 5], p.fp16)), "r"(pack16(acc[8 * j + 6], acc[8 * j + 7], p.fp16))
+                                 "r"(pack16t<F16>(acc[8 * j], acc[8 * j + 1])), "r"(pack16t<F16>(acc[8 * j + 2], acc[8 * j + 3])),
+                                 "r"(pack16t<F16>(acc[8 * j + 4], acc[8 * j + 5])), "r"(pack16t<F16>(acc[8 * j + 6], acc[8 * j + 7]))
                                  : "memory");
                 }
             }
@@ -236,10 +246,13 @@ head_fused_kernel(const __grid_constant__ CUtensorMap map_s0, const __grid_const
                 tmem_ld_wait();
                 uint32_t o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float a0 = fmaxf(fmaf(__uint_as_float(v[2 * j]), s_sc0[c + 2 * j], s_sh0[c + 2 * j]), 0.f);
-                    const float a1 = fmaxf(fmaf(__uint_as_float(v[2 * j + 1]), s_sc0[c + 2 * j + 1], s_sh0[c + 2 * j + 1]), 0.f);
-                    o[j] = pack16(a0, a1, p.fp16);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_sc0 + c + 4 * j4);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_sh0 + c + 4 * j4);
+                    o[2 * j4] = pack16t<F16>(fmaxf(fmaf(__uint_as_float(v[4 * j4]), sc.x, sh.x), 0.f),
+                                             fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y), 0.f));
+                    o[2 * j4 + 1] = pack16t<F16>(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z), 0.f),
+                                                 fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w), 0.f));
                 }
                 // 128-byte swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
                 const uint32_t j0 = (uint32_t)(c >> 3);
@@ -270,11 +283,20 @@ head_fused_kernel(const __grid_constant__ CUtensorMap map_s0, const __grid_const
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float fv = fmaxf(fmaf(__uint_as_float(v[j]), s_sc1[c0 + j], s_sh1[c0 + j]), 0.f);
-                    const float* wr = s_wl + (c0 + j) * 8;
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_sc1 + c0 + 4 * j4);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_sh1 + c0 + 4 * j4);
+                    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) lg[c] = fmaf(fv, wr[c], lg[c]);
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = 4 * j4 + u;
+                        const float fv = fmaxf(fmaf(__uint_as_float(v[j]), scv[u], shv[u]), 0.f);
+                        const float4 wa = *reinterpret_cast<const float4*>(s_wl + (c0 + j) * 8);
+                        const float4 wb = *reinterpret_cast<const float4*>(s_wl + (c0 + j) * 8 + 4);
+                        const float wr[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) lg[c] = fmaf(fv, wr[c], lg[c]);
+                    }
                 }
             }
             tc_fence_before();

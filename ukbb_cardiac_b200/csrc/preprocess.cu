@@ -110,34 +110,61 @@ sel_histn_kernel(const float* __restrict__ vol, long long n, const SelState* __r
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) vote(vol[(n4 << 2) + threadIdx.x]);
 }
 
-// After each pass: locate, for every rank, the bin holding it (one warp per rank, serial scan by
-// lane 0 is plenty: <= 4096 bins).  Ranks that share a prefix share the histogram of the first.
+// After each pass: locate, for every rank, the bin holding it.  One 1024-thread block: every thread
+// owns bins/1024 consecutive bins, a shared-memory inclusive scan finds the owning thread.  Ranks that
+// share a prefix share the histogram of the first such rank.
 template <int PASS>
-__global__ void sel_scan_kernel(SelState* st, const unsigned int* __restrict__ hist) {
-    const int r = threadIdx.x;          // launched with one warp; lanes >= NRANK idle
-    unsigned int pre[NRANK];
-    for (int q = 0; q < NRANK; ++q) pre[q] = st->prefix[q];
-    __syncwarp();                       // every lane has read the prefixes before any update
-    if (r < NRANK) {
+__global__ void __launch_bounds__(1024)
+sel_scan_kernel(SelState* st, const unsigned int* __restrict__ hist) {
+    __shared__ unsigned long long s_scan[1024];
+    __shared__ unsigned int s_pre[NRANK];
+    __shared__ unsigned long long s_newrank[NRANK];
+    __shared__ unsigned int s_newpre[NRANK];
+    const int t = threadIdx.x;
+    if (t < NRANK) s_pre[t] = st->prefix[t];
+    __syncthreads();
+    constexpr int bins = PASS == 2 ? BINS2 : BINS0;
+    constexpr int per = bins >= 1024 ? bins / 1024 : 1;
+    for (int r = 0; r < NRANK; ++r) {
         int src = r;
         if (PASS > 0)
             for (int q = r - 1; q >= 0; --q)
-                if (pre[q] == pre[r]) src = q;
+                if (s_pre[q] == s_pre[r]) src = q;
         const unsigned int* h = PASS == 0 ? hist : PASS == 1 ? hist + BINS0 + src * BINS1
                                                              : hist + BINS0 + NRANK * BINS1 + src * BINS2;
-        const int bins = PASS == 2 ? BINS2 : BINS0;
-        const unsigned long long want = st->rank[r];
-        unsigned long long cum = 0;
-        int b = 0;
-        for (; b < bins - 1; ++b) {
-            const unsigned int c = h[b];
-            if (cum + c > want) break;
-            cum += c;
+        unsigned int c[per];
+        unsigned long long local = 0;
+#pragma unroll
+        for (int i = 0; i < per; ++i) {
+            const int bin = t * per + i;
+            c[i] = bin < bins ? h[bin] : 0u;
+            local += c[i];
         }
-        st->rank[r] = want - cum;
-        st->prefix[r] = PASS == 0 ? (unsigned)b : PASS == 1 ? ((pre[r] << 12) | (unsigned)b)
-                                                            : ((pre[r] << 8) | (unsigned)b);
+        s_scan[t] = local;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            const unsigned long long v = t >= off ? s_scan[t - off] : 0ull;
+            __syncthreads();
+            s_scan[t] += v;
+            __syncthreads();
+        }
+        const unsigned long long incl = s_scan[t], excl = incl - local, want = st->rank[r];
+        const unsigned long long total = s_scan[1023];
+        const bool owner = (want >= excl && want < incl) || (want >= total && t == 1023 && local == 0 && false);
+        if (owner) {
+            unsigned long long cum = excl;
+            int b = t * per;
+#pragma unroll
+            for (int i = 0; i < per; ++i) {
+                if (cum + c[i] > want) { b = t * per + i; break; }
+                cum += c[i];
+            }
+            s_newrank[r] = want - cum;
+            s_newpre[r] = PASS == 0 ? (unsigned)b : PASS == 1 ? ((s_pre[r] << 12) | (unsigned)b) : ((s_pre[r] << 8) | (unsigned)b);
+        }
+        __syncthreads();
     }
+    if (t < NRANK) { st->rank[t] = s_newrank[t]; st->prefix[t] = s_newpre[t]; }
 }
 
 __global__ void sel_final_kernel(const SelState* __restrict__ st, double t_lo, double t_hi,
@@ -230,11 +257,11 @@ int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int 
     const int hgrid = sms * 4;       // 4 resident 512-thread CTAs per SM
     sel_init_kernel<<<16, 256, 0, st>>>(state, ws.hist, rk[0], rk[1], rk[2], rk[3]);
     sel_hist0_kernel<<<hgrid, 512, 0, st>>>(vol, n, ws.hist);
-    sel_scan_kernel<0><<<1, 32, 0, st>>>(state, ws.hist);
+    sel_scan_kernel<0><<<1, 1024, 0, st>>>(state, ws.hist);
     sel_histn_kernel<1><<<hgrid, 512, 0, st>>>(vol, n, state, ws.hist);
-    sel_scan_kernel<1><<<1, 32, 0, st>>>(state, ws.hist);
+    sel_scan_kernel<1><<<1, 1024, 0, st>>>(state, ws.hist);
     sel_histn_kernel<2><<<hgrid, 512, 0, st>>>(vol, n, state, ws.hist);
-    sel_scan_kernel<2><<<1, 32, 0, st>>>(state, ws.hist);
+    sel_scan_kernel<2><<<1, 1024, 0, st>>>(state, ws.hist);
     sel_final_kernel<<<1, 32, 0, st>>>(state, t[0], t[1], ws.vlvh, ws.sel, vl_vh_out);
     const long long total4 = n_slices * y2 * (x2 / 4);
     rescale_pad_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(vol, out, ws.vlvh, total4, x, y, x2, y2,

@@ -97,6 +97,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, with the descriptors given as (lo, hi) 32-bit halves so that a K / tap / window advance
+// is a single 32-bit add on the low word (start address field, 16-byte units).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -144,6 +160,19 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
         return *reinterpret_cast<uint32_t*>(&h);
     }
     return pack_bf16(a, b);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16t(float a, float b) {
+    if (F16) {
+        __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));      // inputs are >= 0 (post-ReLU) or small
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    return pack_bf16(a, b);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16t(uint32_t u) {
+    if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 __device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {
     if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
