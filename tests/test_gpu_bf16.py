@@ -137,11 +137,16 @@ def test_fused_and_unfused_paths_agree(monkeypatch):
     with FCNEngine(w, mode="fp16") as eng:
         l1, g1, _ = eng.forward(dev, want_logits=True)
         torch.cuda.synchronize()
+    monkeypatch.setenv("UKBB_HEAD_GATHER", "1")          # head v1: 4-tap gather on CUDA cores
+    with FCNEngine(w, mode="fp16") as eng:
+        l3, g3, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
     monkeypatch.setenv("UKBB_NO_FUSED_HEAD", "1")
     monkeypatch.setenv("UKBB_NO_HALO", "1")
     with FCNEngine(w, mode="fp16") as eng:
         l2, g2, _ = eng.forward(dev, want_logits=True)
         torch.cuda.synchronize()
-    rel = float((g1 - g2).abs().max() / g2.abs().max())
-    assert rel < 5e-3, rel
-    assert float((l1 == l2).float().mean()) >= 0.998
+    for g, l, name in ((g1, l1, "tensor-core upsample head"), (g3, l3, "gather head")):
+        rel = float((g - g2).abs().max() / g2.abs().max())
+        assert rel < 5e-3, (name, rel)
+        assert float((l == l2).float().mean()) >= 0.998, name

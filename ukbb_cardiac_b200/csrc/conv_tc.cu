@@ -18,6 +18,7 @@
 #include "tc_common.cuh"
 #include "conv_halo.cuh"
 #include "head_fused.cuh"
+#include "head_mma.cuh"
 #include <stdlib.h>
 #include <vector>
 #include <string.h>
@@ -28,6 +29,7 @@ using namespace tc;
 
 struct ConvTcParams {
     int taps, ks, stride, cin;
+    int kofs;                       // first K column of the weight matrix (sub-matrix selection)
     int pad_top, pad_left;
     int bw, bh, bn;                 // output box of one tile: bw * bh * bn == 128
     int tiles_x, tiles_y, n_tiles;
@@ -106,7 +108,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint32_t b_dst = a_dst + Cfg::A_BYTES;
                     mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
                     tma_load_4d(a_dst, &map_a, full_bar(stage), ch * CC, x0 + kx, y0 + ky, n0);
-                    tma_load_2d(b_dst, &map_b, full_bar(stage), tap * p.cin + ch * CC, 0);
+                    tma_load_2d(b_dst, &map_b, full_bar(stage), p.kofs + tap * p.cin + ch * CC, 0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -377,8 +379,13 @@ struct Bf16State {
     TcLayerPlan plan[UKBB_N_CONV];
     int plan_nb = 0, plan_h = 0, plan_w = 0;
     int fp16 = 0;
-    int fused_head = 1;
+    int fused_head = 2;                      // 0 = unfused, 1 = gather head (head_fused), 2 = tensor-core upsample (head_mma)
     CUtensorMap map_s0, map_w0, map_w1;      // fused head operands
+    __nv_bfloat16* t[5] = {};                // t_l = W_l . s_l at level l (64 channels), l = 1..4
+    __nv_bfloat16* u[5] = {};                // interpolation matrices U_l (16-bit, exact)
+    float* ones = nullptr;                   // [64] ones then [64] zeros
+    TcLayerPlan tplan[5];
+    HeadMmaMaps hm;
 };
 
 static CUtensorMapSwizzle swizzle_for(int cc) {
@@ -404,7 +411,7 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     while (wo % bw != 0 && bw > 1) bw >>= 1;
     const int bn = 128 / (bw * bh);
     ConvTcParams& p = P.p;
-    p.taps = ks * ks; p.ks = ks; p.stride = s; p.cin = L.cin; p.pad_top = pt; p.pad_left = pl;
+    p.taps = ks * ks; p.ks = ks; p.stride = s; p.cin = L.cin; p.kofs = 0; p.pad_top = pt; p.pad_left = pl;
     p.bw = bw; p.bh = bh; p.bn = bn;
     p.tiles_x = wo / bw; p.tiles_y = ho / bh;
     p.ho = ho; p.wo = wo; p.n = nb; p.relu = L.relu; p.scale = L.scale; p.shift = L.shift; p.out = out;
@@ -517,7 +524,36 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
     if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return UKBB_E_CUDA; }
     S->encode = (EncodeTiledFn)fn;
     S->fp16 = h->mode == UKBB_MODE_FP16 ? 1 : 0;
-    S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : 1;
+    S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : (getenv("UKBB_HEAD_GATHER") ? 1 : 2);
+    {   // interpolation matrices of the tensor-core upsample (see head_mma.cuh) and identity scale / zero shift
+        std::vector<float> oz(128, 0.f);
+        for (int i = 0; i < 64; ++i) oz[i] = 1.f;
+        UKBB_CUDA(cudaMalloc(&S->ones, 128 * sizeof(float)));
+        UKBB_CUDA(cudaMemcpy(S->ones, oz.data(), 128 * sizeof(float), cudaMemcpyHostToDevice));
+        for (int l = 1; l <= 4; ++l) {
+            const int f = 1 << l, pb = (f - 1) / 2, kpad = HM_KPAD[l], pw = HM_PW[l], nv = l == 4 ? 2 : 1;
+            std::vector<__nv_bfloat16> U((size_t)nv * 128 * kpad);
+            std::vector<float> Uf((size_t)nv * 128 * kpad, 0.f);
+            for (int v = 0; v < nv; ++v)
+                for (int m = 0; m < 128; ++m) {
+                    const int ty = m >> 4, tx = m & 15;
+                    const int Y = (l == 4 ? 8 * v : 0) + ty + pb, X = tx + pb;
+                    const int ry = Y & (f - 1), py1 = (Y >> l) + 1, rx = X & (f - 1), px1 = (X >> l) + 1;
+                    const float wy1 = (float)(ry + 1) / (float)f, wy0 = 1.f - wy1, wx1 = (float)(rx + 1) / (float)f, wx0 = 1.f - wx1;
+                    float* row = &Uf[((size_t)v * 128 + m) * kpad];
+                    row[(py1 - 1) * pw + (px1 - 1)] += wy0 * wx0;
+                    row[(py1 - 1) * pw + px1] += wy0 * wx1;
+                    row[py1 * pw + (px1 - 1)] += wy1 * wx0;
+                    row[py1 * pw + px1] += wy1 * wx1;
+                }
+            for (size_t i = 0; i < U.size(); ++i) {
+                if (S->fp16) { const __half hv = __float2half_rn(Uf[i]); memcpy(&U[i], &hv, 2); }
+                else U[i] = __float2bfloat16(Uf[i]);
+            }
+            UKBB_CUDA(cudaMalloc(&S->u[l], U.size() * 2));
+            UKBB_CUDA(cudaMemcpy(S->u[l], U.data(), U.size() * 2, cudaMemcpyHostToDevice));
+        }
+    }
     for (int i = 1; i < UKBB_N_CONV - 1; ++i) {
         const ukbb_conv_weights& c = w->conv[i];
         const int taps = c.ksize * c.ksize, ktot = taps * c.cin;
@@ -543,6 +579,8 @@ void bf16_release(Engine* h) {
     if (!S) return;
     for (int i = 0; i < UKBB_N_CONV; ++i) cudaFree(S->w[i]);
     cudaFree(S->w0); cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
+    for (int l = 0; l < 5; ++l) { cudaFree(S->t[l]); cudaFree(S->u[l]); }
+    cudaFree(S->ones);
     delete S;
     h->tc = nullptr;
 }
@@ -566,9 +604,15 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
     cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
     S->cat = S->f0 = S->f1 = nullptr;
     const size_t px = (size_t)nb * h2 * w2;
-    UKBB_CUDA(cudaMalloc(&S->cat, px * 160 * 2));
-    UKBB_CUDA(cudaMalloc(&S->f0, px * 64 * 2));
-    UKBB_CUDA(cudaMalloc(&S->f1, px * 64 * 2));
+    if (S->fused_head == 0) {
+        UKBB_CUDA(cudaMalloc(&S->cat, px * 160 * 2));
+        UKBB_CUDA(cudaMalloc(&S->f0, px * 64 * 2));
+        UKBB_CUDA(cudaMalloc(&S->f1, px * 64 * 2));
+    }
+    for (int l = 1; l <= 4; ++l) {
+        cudaFree(S->t[l]); S->t[l] = nullptr;
+        if (S->fused_head == 2) UKBB_CUDA(cudaMalloc(&S->t[l], (size_t)nb * (h2 >> l) * (w2 >> l) * 64 * 2));
+    }
     h->ws.nb = nb; h->ws.h = h2; h->ws.w = w2;
     int li = 0, rc;
     const __nv_bfloat16* cur = nullptr;
@@ -590,10 +634,55 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
         rc = make_plan(h, li, level_out[l], (__nv_bfloat16*)h->ws.s[l], nb, h2 >> l, w2 >> l, l);
         if (rc) return rc;
     }
-    rc = make_plan(h, 18, S->cat, S->f0, nb, h2, w2, 0);
-    if (rc) return rc;
-    rc = make_plan(h, 19, S->f0, S->f1, nb, h2, w2, 0);
-    if (rc) return rc;
+    if (S->fused_head == 0) {
+        rc = make_plan(h, 18, S->cat, S->f0, nb, h2, w2, 0);
+        if (rc) return rc;
+        rc = make_plan(h, 19, S->f0, S->f1, nb, h2, w2, 0);
+        if (rc) return rc;
+    }
+    if (S->fused_head == 2) {
+        const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        const CUtensorMapSwizzle sw128 = CU_TENSOR_MAP_SWIZZLE_128B;
+        cuuint32_t e4[4] = {1, 1, 1, 1}, e2[2] = {1, 1};
+        CUtensorMap* tm[5] = {nullptr, &S->hm.t1, &S->hm.t2, &S->hm.t3, &S->hm.t4};
+        CUtensorMap* um[5] = {nullptr, &S->hm.u1, &S->hm.u2, &S->hm.u3, &S->hm.u4};
+        for (int l = 1; l <= 4; ++l) {
+            // t_l = W_l . s_l : 1x1 conv 32 -> 64 on the same_dim output of level l, columns [32 l, 32 l + 32) of W_fc0
+            TcLayerPlan saved = S->plan[18];
+            const ConvLayer keep = h->layers[18];
+            ConvLayer& L = h->layers[18];
+            L.cin = 32; L.relu = 0; L.scale = S->ones; L.shift = S->ones + 64;
+            rc = make_plan(h, 18, (const __nv_bfloat16*)h->ws.s[l], S->t[l], nb, h2 >> l, w2 >> l, l);
+            h->layers[18] = keep;
+            if (rc) { S->plan[18] = saved; return rc; }
+            S->tplan[l] = S->plan[18];
+            S->plan[18] = saved;
+            S->tplan[l].p.kofs = 32 * l;
+            {   // weight map must span all 160 K columns: rebuild it (make_plan used cin = 32)
+                cuuint64_t d0[2] = {160, 64}; cuuint64_t st0[1] = {320}; cuuint32_t b0[2] = {32, 64};
+                CUresult r = S->encode(&S->tplan[l].map_b, dt16, 2, S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(t-layer weights) failed: %d", (int)r); return UKBB_E_CUDA; }
+            }
+            {   // t_l patches for the head: [nb][h_l][w_l][64], box (64, PW, PH, 1)
+                cuuint64_t dims[4] = {64, (cuuint64_t)(w2 >> l), (cuuint64_t)(h2 >> l), (cuuint64_t)nb};
+                cuuint64_t strides[3] = {128, (cuuint64_t)(w2 >> l) * 128, (cuuint64_t)(h2 >> l) * (w2 >> l) * 128};
+                cuuint32_t box[4] = {64, (cuuint32_t)HM_PW[l], (cuuint32_t)HM_PH[l], 1};
+                CUresult r = S->encode(tm[l], dt16, 4, S->t[l], dims, strides, box, e4, CU_TENSOR_MAP_INTERLEAVE_NONE, sw128,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(t patch %d) failed: %d", l, (int)r); return UKBB_E_CUDA; }
+            }
+            {   // U_l: [nv * 128][kpad]
+                const int kpad = HM_KPAD[l], nv = l == 4 ? 2 : 1;
+                cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)(nv * 128)};
+                cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+                cuuint32_t box[2] = {(cuuint32_t)kpad, 128};
+                CUresult r = S->encode(um[l], dt16, 2, S->u[l], dims, strides, box, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       swizzle_for(kpad), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(U %d) failed: %d", l, (int)r); return UKBB_E_CUDA; }
+            }
+        }
+    }
     {   // fused head operands: s0 tiles (8 rows x 16 columns x 32 channels), fc0 / fc1 weights
         const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         cuuint64_t dims[4] = {32, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)nb};
@@ -611,6 +700,7 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
             r = S->encode(&S->map_w1, dt16, 2, S->w[19], d1, st1, b1, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(fused head) failed: %d", (int)r); return UKBB_E_CUDA; }
+        S->hm.s0 = S->map_s0; S->hm.w0 = S->map_w0; S->hm.w1 = S->map_w1;
     }
     S->plan_nb = nb; S->plan_h = h2; S->plan_w = w2;
     return UKBB_OK;
@@ -628,8 +718,21 @@ static int launch_head2(const Bf16State* S, const HeadParams& hp, int sms, cudaS
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
 }
+template <int NC, bool F16>
+static int launch_head_mma2(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(head_mma_kernel<NC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HM_SMEM));
+        attr_set = true;
+    }
+    const int grid = hp.n_tiles < sms ? hp.n_tiles : sms;
+    head_mma_kernel<NC, F16><<<grid, HM_THREADS, HM_SMEM, st>>>(S->hm, hp);
+    UKBB_CUDA(cudaGetLastError());
+    return UKBB_OK;
+}
 template <int NC>
 static int launch_head(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+    if (S->fused_head == 2) return S->fp16 ? launch_head_mma2<NC, true>(S, hp, sms, st) : launch_head_mma2<NC, false>(S, hp, sms, st);
     return S->fp16 ? launch_head2<NC, true>(S, hp, sms, st) : launch_head2<NC, false>(S, hp, sms, st);
 }
 
@@ -677,6 +780,16 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             rc = launch_plan(P, h->sms, st);
             if (rc) return rc;
             h->launches++;
+        }
+        if (S->fused_head == 2) {
+            for (int l = 1; l <= 4; ++l) {
+                TcLayerPlan P = S->tplan[l];
+                P.p.n = nb;
+                P.p.n_tiles = P.p.tiles_x * P.p.tiles_y * ((nb + P.p.bn - 1) / P.p.bn);
+                rc = launch_plan(P, h->sms, st);
+                if (rc) return rc;
+                h->launches++;
+            }
         }
         if (S->fused_head) {
             HeadParams hp;
