@@ -701,6 +701,19 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(fused head) failed: %d", (int)r); return UKBB_E_CUDA; }
         S->hm.s0 = S->map_s0; S->hm.w0 = S->map_w0; S->hm.w1 = S->map_w1;
+        if (S->fused_head == 2) {
+            // head_mma computes same_dim0 itself: its level-0 input is the conv0_1 output (16 channels)
+            cuuint64_t dimsb[4] = {16, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)nb};
+            cuuint64_t stridesb[3] = {32, (cuuint64_t)w2 * 32, (cuuint64_t)h2 * w2 * 32};
+            cuuint32_t boxb[4] = {16, 16, 8, 1};
+            r = S->encode(&S->hm.s0, dt16, 4, h->ws.b[0], dimsb, stridesb, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            cuuint64_t dsd[2] = {16, 32}; cuuint64_t ssd[1] = {32}; cuuint32_t bsd[2] = {16, 32};
+            if (r == CUDA_SUCCESS)
+                r = S->encode(&S->hm.wsd, dt16, 2, S->w[13], dsd, ssd, bsd, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(head same_dim0) failed: %d", (int)r); return UKBB_E_CUDA; }
+        }
     }
     S->plan_nb = nb; S->plan_h = h2; S->plan_w = w2;
     return UKBB_OK;
@@ -772,6 +785,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             h->launches++;
         }
         for (int li = 1; li < 18; ++li) {
+            if (li == 13 && S->fused_head == 2) continue;        // same_dim0 lives inside head_mma_kernel
             TcLayerPlan P = S->plan[li];
             P.p.n = nb;
             P.p.n_tiles = P.p.tiles_x * P.p.tiles_y * ((nb + P.p.bn - 1) / P.p.bn);
@@ -800,6 +814,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             hp.fp16 = S->fp16; hp.nc = h->n_class;
             hp.scale0 = h->layers[18].scale; hp.shift0 = h->layers[18].shift;
             hp.scale1 = h->layers[19].scale; hp.shift1 = h->layers[19].shift;
+            hp.scale_sd0 = h->layers[13].scale; hp.shift_sd0 = h->layers[13].shift;
             hp.wlog = h->layers[20].w_f32; hp.blog = h->layers[20].shift;
             const size_t po = (size_t)n0 * h2 * w2 * h->n_class;
             hp.labels = labels + (size_t)n0 * x * y;

@@ -31,6 +31,7 @@ struct HeadParams {
     int fp16, nc;
     const float* scale0; const float* shift0;     // fc0 BN fold
     const float* scale1; const float* shift1;     // fc1 BN fold
+    const float* scale_sd0; const float* shift_sd0;   // same_dim0 BN fold (head_mma only)
     const float* wlog;              // [64][nc] fp32
     const float* blog;              // [nc]
     uint8_t* labels;                // [n][y][x]

@@ -32,18 +32,21 @@ constexpr int HM_PH[5] = {0, 5, 4, 3, 3};          // source patch height (y) pe
 constexpr int HM_KPAD[5] = {32, 64, 32, 16, 16};   // padded K of the U_l matrices (level 0: s0 channels)
 constexpr int HM_KSTEPS[5] = {2, 3, 2, 1, 1};      // UMMA K-steps (16 each) actually issued
 // shared-memory layout (bytes)
-constexpr int HM_IN_S0 = 8192;                                    // s0 tile [128][64 B]
+constexpr int HM_IN_S0 = 4096;                                    // b0 tile [128 pixels][16 ch = 32 B] (input of same_dim0)
 constexpr int HM_IN_P1 = 48 * 128, HM_IN_P2 = 32 * 128, HM_IN_P3 = 16 * 128, HM_IN_P4 = 16 * 128;
-constexpr int HM_IN_BYTES = HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3 + HM_IN_P4;   // 22528
+constexpr int HM_IN_BYTES = HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3 + HM_IN_P4;
 constexpr int HM_IN_TX = HM_IN_S0 + (45 + 24 + 12 + 9) * 128;     // bytes TMA actually delivers per tile
+constexpr int HM_A0 = 128 * 64;                                   // same_dim0 output tile as fc0 A operand [128][64 B]
 constexpr int HM_A2 = 128 * 128;
 constexpr int HM_U1 = 128 * 128, HM_U2 = 128 * 64, HM_U3 = 128 * 32, HM_U4 = 2 * 128 * 32;
 constexpr int HM_U_BYTES = HM_U1 + HM_U2 + HM_U3 + HM_U4;         // 36864
-constexpr int HM_W0 = 64 * 64, HM_W1 = 64 * 128;
-constexpr int HM_SMEM = 2 * HM_IN_BYTES + 2 * HM_A2 + HM_U_BYTES + HM_W0 + HM_W1 + 1024 + 256 + (4 * 64 + 64 * 8 + 8) * 4;
+constexpr int HM_W0 = 64 * 64, HM_W1 = 64 * 128, HM_WSD = 1024;     // fc0 level-0 slice, fc1, same_dim0 [32][16]
+constexpr int HM_IN_STAGES = 3;
+constexpr int HM_SMEM = HM_IN_STAGES * HM_IN_BYTES + 2 * HM_A0 + 2 * HM_A2 + HM_U_BYTES + HM_W0 + HM_W1 + HM_WSD + 1024 + 256 +
+                        (4 * 64 + 64 * 8 + 8 + 64) * 4;
 
 struct HeadMmaMaps {
-    CUtensorMap s0, t1, t2, t3, t4, u1, u2, u3, u4, w0, w1;
+    CUtensorMap s0 /* b0: conv0 output, 16 ch */, t1, t2, t3, t4, u1, u2, u3, u4, w0, w1, wsd;
 };
 
 template <int NC, bool F16>
@@ -54,38 +57,44 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t in_base = smem_base;                           // 2 stages of inputs
-    const uint32_t a2_base = in_base + 2 * HM_IN_BYTES;           // 2 x 16 KB
+    const uint32_t a0_base = in_base + HM_IN_STAGES * HM_IN_BYTES;   // 2 x 8 KB
+    const uint32_t a2_base = a0_base + 2 * HM_A0;                 // 2 x 16 KB
     const uint32_t u_base = a2_base + 2 * HM_A2;
     const uint32_t w0_base = u_base + HM_U_BYTES;
     const uint32_t w1_base = w0_base + HM_W0;
-    const uint32_t bar_base = w1_base + HM_W1;
+    const uint32_t wsd_base = w1_base + HM_W1;
+    const uint32_t bar_base = wsd_base + HM_WSD;
     auto BAR = [&](int i) { return bar_base + 8u * i; };
     // 0 wfull | 1,2 in_full | 3,4 in_empty | 5,6 d1_full | 7,8 d1_empty | 9,10 a2_full | 11,12 a2_empty |
-    // 13,14 d2_full | 15,16 d2_empty | 17 tmem slot
-    const uint32_t tmem_slot = BAR(17);
+    // 13,14 d2_full | 15,16 d2_empty | 17,18 d0_full | 19,20 d0_empty | 21,22 a0_full | 23,24 a0_empty | 25 tmem slot
+    // 26,27,28 in_full (3 input stages) | 29,30,31 in_empty      (slots 1-4 unused)
+    const uint32_t tmem_slot = BAR(25);
     float* s_f = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 256);
     float* s_sc0 = s_f; float* s_sh0 = s_f + 64; float* s_sc1 = s_f + 128; float* s_sh1 = s_f + 192;
     float* s_wl = s_f + 256;
     float* s_bl = s_f + 256 + 512;
+    float* s_scd = s_f + 256 + 512 + 8;       // same_dim0 BN fold: scale[32], shift[32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 8 && lane == 0) {
         const CUtensorMap* m = &maps.s0;
-        for (int i = 0; i < 11; ++i) tma_prefetch_desc(m + i);
+        for (int i = 0; i < 12; ++i) tma_prefetch_desc(m + i);
     }
     if (warp == 9 && lane == 0) {
         mbar_init(BAR(0), 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(BAR(1 + b), 1);  mbar_init(BAR(3 + b), 1);  mbar_init(BAR(5 + b), 1);  mbar_init(BAR(7 + b), 4);
             mbar_init(BAR(9 + b), 4);  mbar_init(BAR(11 + b), 1); mbar_init(BAR(13 + b), 1); mbar_init(BAR(15 + b), 4);
+            mbar_init(BAR(17 + b), 1); mbar_init(BAR(19 + b), 4); mbar_init(BAR(21 + b), 4); mbar_init(BAR(23 + b), 1);
         }
+        for (int s3 = 0; s3 < HM_IN_STAGES; ++s3) { mbar_init(BAR(26 + s3), 1); mbar_init(BAR(29 + s3), 1); }
         fence_barrier_init();
     }
-    if (warp == 8) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     // zero the input stages once: the K-padding rows of the t_l patches are never written by TMA and
     // must be finite (they meet zero columns of U_l)
-    for (int i = threadIdx.x; i < 2 * HM_IN_BYTES / 16; i += HM_THREADS)
+    for (int i = threadIdx.x; i < HM_IN_STAGES * HM_IN_BYTES / 16; i += HM_THREADS)
         reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < 64; i += HM_THREADS) {
         s_sc0[i] = p.scale0[i]; s_sh0[i] = p.shift0[i]; s_sc1[i] = p.scale1[i]; s_sh1[i] = p.shift1[i];
@@ -95,6 +104,7 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
         s_wl[i] = c < p.nc ? p.wlog[k * p.nc + c] : 0.f;
     }
     if (threadIdx.x < 8) s_bl[threadIdx.x] = threadIdx.x < p.nc ? p.blog[threadIdx.x] : -INFINITY;
+    if (threadIdx.x < 32) { s_scd[threadIdx.x] = p.scale_sd0[threadIdx.x]; s_scd[32 + threadIdx.x] = p.shift_sd0[threadIdx.x]; }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -107,7 +117,8 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(BAR(0), HM_U_BYTES + HM_W0 + HM_W1);
+            mbar_arrive_expect_tx(BAR(0), HM_U_BYTES + HM_W0 + HM_W1 + HM_WSD);
+            tma_load_2d(wsd_base, &maps.wsd, BAR(0), 0, 0);
             tma_load_2d(u_base, &maps.u1, BAR(0), 0, 0);
             tma_load_2d(u_base + HM_U1, &maps.u2, BAR(0), 0, 0);
             tma_load_2d(u_base + HM_U1 + HM_U2, &maps.u3, BAR(0), 0, 0);
@@ -117,19 +128,20 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
             tma_load_2d(w1_base, &maps.w1, BAR(0), 0, 0);
             for (int i = 0; i < my_tiles; ++i) {
                 const int tile = blockIdx.x + i * gridDim.x;
-                const int b = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
+                const int s3 = i % HM_IN_STAGES;
+                const uint32_t ph = (uint32_t)(i / HM_IN_STAGES) & 1u;
                 const int n = tile / tiles_per_slice, t2 = tile - n * tiles_per_slice;
                 const int y0 = (t2 / p.tiles_x) * 8, x0 = (t2 % p.tiles_x) * 16;
-                mbar_wait(BAR(3 + b), ph ^ 1);
-                const uint32_t dst = in_base + b * HM_IN_BYTES;
-                mbar_arrive_expect_tx(BAR(1 + b), HM_IN_TX);
-                tma_load_4d(dst, &maps.s0, BAR(1 + b), 0, x0, y0, n);
+                mbar_wait(BAR(29 + s3), ph ^ 1);
+                const uint32_t dst = in_base + s3 * HM_IN_BYTES;
+                const uint32_t fullb = BAR(26 + s3);
+                mbar_arrive_expect_tx(fullb, HM_IN_TX);
+                tma_load_4d(dst, &maps.s0, fullb, 0, x0, y0, n);
                 // level l patch origin: ((x0 + pb) >> l) - 1, pb = (2^l - 1) / 2
-                tma_load_4d(dst + HM_IN_S0, &maps.t1, BAR(1 + b), 0, (x0 >> 1) - 1, (y0 >> 1) - 1, n);
-                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1, &maps.t2, BAR(1 + b), 0, ((x0 + 1) >> 2) - 1, ((y0 + 1) >> 2) - 1, n);
-                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1 + HM_IN_P2, &maps.t3, BAR(1 + b), 0, ((x0 + 3) >> 3) - 1, ((y0 + 3) >> 3) - 1, n);
-                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3, &maps.t4, BAR(1 + b), 0, ((x0 + 7) >> 4) - 1,
+                tma_load_4d(dst + HM_IN_S0, &maps.t1, fullb, 0, (x0 >> 1) - 1, (y0 >> 1) - 1, n);
+                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1, &maps.t2, fullb, 0, ((x0 + 1) >> 2) - 1, ((y0 + 1) >> 2) - 1, n);
+                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1 + HM_IN_P2, &maps.t3, fullb, 0, ((x0 + 3) >> 3) - 1, ((y0 + 3) >> 3) - 1, n);
+                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3, &maps.t4, fullb, 0, ((x0 + 7) >> 4) - 1,
                             ((y0 + 7) >> 4) - 1, n);
             }
         }
@@ -144,24 +156,41 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
         auto LO = [](uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); };
         const uint32_t u1_lo = LO(u_base), u2_lo = LO(u_base + HM_U1), u3_lo = LO(u_base + HM_U1 + HM_U2),
                        u4_lo = LO(u_base + HM_U1 + HM_U2 + HM_U3);
-        const uint32_t w0_lo = LO(w0_base), w1_lo = LO(w1_base);
+        const uint32_t w0_lo = LO(w0_base), w1_lo = LO(w1_base), wsd_lo = LO(wsd_base);
+        const uint32_t idesc_sd = F16 ? make_idesc_f16(128, 32) : make_idesc_bf16(128, 32);
         mbar_wait(BAR(0), 0);
         tc_fence_after();
+        // same_dim0 (network.py:201-204, level 0): D0[128 x 32] = b0_tile[128 x 16] . Wsd0^T
+        auto issue0 = [&](int i) {
+            const int b = i & 1;
+            const uint32_t ph = (i >> 1) & 1;
+            const int s3 = i % HM_IN_STAGES;
+            mbar_wait(BAR(26 + s3), (uint32_t)(i / HM_IN_STAGES) & 1u);
+            mbar_wait(BAR(19 + b), ph ^ 1);
+            tc_fence_after();
+            if (leader) {
+                umma_bf16_lohi(tmem_base + 256 + b * 32, LO(in_base + s3 * HM_IN_BYTES), HI32, wsd_lo, HI32, idesc_sd, 0u);
+                umma_commit(BAR(17 + b));
+            }
+            __syncwarp();
+        };
         auto issue1 = [&](int i) {
             const int b = i & 1;
             const uint32_t ph = (i >> 1) & 1;
             const int tile = blockIdx.x + i * gridDim.x;
             const int t2 = tile % tiles_per_slice;
             const uint32_t v = (uint32_t)((t2 / p.tiles_x) & 1);                 // tile-row parity selects the U_4 variant
-            mbar_wait(BAR(1 + b), ph);
+            mbar_wait(BAR(21 + b), ph);
             mbar_wait(BAR(7 + b), ph ^ 1);
             tc_fence_after();
             const uint32_t d = tmem_base + b * 64;
-            const uint32_t in_lo = LO(in_base + b * HM_IN_BYTES);
+            const int s3 = i % HM_IN_STAGES;
+            const uint32_t in_lo = LO(in_base + s3 * HM_IN_BYTES);
+            const uint32_t a0_lo = LO(a0_base + b * HM_A0);
             if (leader) {
-                // level 0: s0 tile (K-major, 64 B rows) x W_0 (K-major)
-                umma_bf16_lohi(d, in_lo, HI64, w0_lo, HI64, idesc_kk, 0u);
-                umma_bf16_lohi(d, in_lo + 2, HI64, w0_lo + 2, HI64, idesc_kk, 1u);
+                // level 0: same_dim0 tile (written by epilogue 0, K-major, 64 B rows) x W_0 (K-major)
+                umma_bf16_lohi(d, a0_lo, HI64, w0_lo, HI64, idesc_kk, 0u);
+                umma_bf16_lohi(d, a0_lo + 2, HI64, w0_lo + 2, HI64, idesc_kk, 1u);
                 // level 1: U_1 [128][64] (128 B rows), 3 K-steps; B = patch rows 16k.. (128 B per source pixel)
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
@@ -172,7 +201,8 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
                 umma_bf16_lohi(d, u3_lo, HI32, in_lo + ((HM_IN_S0 + HM_IN_P1 + HM_IN_P2) >> 4), HI128, idesc_kmn, 1u);
                 umma_bf16_lohi(d, u4_lo + v * ((128 * 32) >> 4), HI32, in_lo + ((HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3) >> 4), HI128,
                                idesc_kmn, 1u);
-                umma_commit(BAR(3 + b));
+                umma_commit(BAR(29 + s3));
+                umma_commit(BAR(23 + b));
                 umma_commit(BAR(5 + b));
             }
             __syncwarp();
@@ -193,8 +223,11 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
             }
             __syncwarp();
         };
+        if (my_tiles > 0) issue0(0);
+        if (my_tiles > 1) issue0(1);
         if (my_tiles > 0) issue1(0);
         for (int i = 0; i < my_tiles; ++i) {
+            if (i + 2 < my_tiles) issue0(i + 2);
             if (i + 1 < my_tiles) issue1(i + 1);
             issue2(i);
         }
@@ -202,7 +235,43 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
         // ===================== epilogue 1: D1 -> BN + ReLU -> 16-bit A2 (128 B swizzle) =====================
         const int q = warp;
         const int r = q * 32 + lane;
+        // epilogue 0: D0 -> same_dim0 BN + ReLU -> 16-bit A0 tile (64 B rows, 64-byte swizzle)
+        auto ep0 = [&](int i) {
+            const int b = i & 1;
+            const uint32_t ph = (i >> 1) & 1;
+            mbar_wait(BAR(17 + b), ph);
+            mbar_wait(BAR(23 + b), ph ^ 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256 + b * 32;
+            const uint32_t row = a0_base + b * HM_A0 + r * 64;
+#pragma unroll
+            for (int c = 0; c < 32; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_ld_wait();
+                uint32_t o[8];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_scd + c + 4 * j4);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_scd + 32 + c + 4 * j4);
+                    o[2 * j4] = pack16t<F16>(fmaxf(fmaf(__uint_as_float(v[4 * j4]), sc.x, sh.x), 0.f),
+                                             fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y), 0.f));
+                    o[2 * j4 + 1] = pack16t<F16>(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z), 0.f),
+                                                 fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w), 0.f));
+                }
+                const uint32_t j0 = (uint32_t)(c >> 3), sw = ((uint32_t)r >> 1) & 3u;
+                const uint32_t d0 = row + ((j0 ^ sw) << 4), d1 = row + (((j0 + 1) ^ sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(BAR(19 + b)); mbar_arrive(BAR(21 + b)); }
+        };
+        if (my_tiles > 0) ep0(0);
         for (int i = 0; i < my_tiles; ++i) {
+            if (i + 1 < my_tiles) ep0(i + 1);
             const int b = i & 1;
             const uint32_t ph = (i >> 1) & 1;
             mbar_wait(BAR(5 + b), ph);
@@ -311,7 +380,7 @@ head_mma_kernel(const __grid_constant__ HeadMmaMaps maps, const HeadParams p) {
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
