@@ -1,0 +1,274 @@
+// 3x3 convolution (stride 1 or 2) + folded BN + ReLU on tcgen05 with PIXEL-GROUP ROWS
+// (north_star (a); network.py:19-25 for the op, :184-188 for the stride-2 layers).
+//
+// Measured on B200 (profiles/r1_rate_probe.log): an M=128, K=16 tcgen05.mma from shared memory
+// costs max(~48, N/2) cycles, so with N = Cout = 16 / 32 the tensor pipe idles 5/6 resp. 2/3 of
+// the time; TMA moves <= 1 box row per cycle, so 32-byte rows cap it at ~30 B/cycle/SM.  Both
+// problems go away when one shared-memory ROW holds G = 64 / Cin horizontally adjacent pixels
+// (always 128 bytes, 128-byte swizzle) and one UMMA row produces the G (stride 1) or G/2
+// (stride 2) output pixels of that group at once:
+//     N = Gout x Cout = 64 for every layer up to 64 channels,
+//     K = the input pixels the group touches along x (G+2 for stride 1, G+1 for stride 2) x Cin,
+// with the 3x3 taps placed block-wise in an expanded weight matrix (zero blocks where a tap does
+// not connect an input pixel of the slice to an output pixel of the group).  Each K-slice (one
+// input pixel of the window) is one UMMA whose A descriptor is just a byte offset into the halo
+// patch: row offset -1/0/+1 groups, sub-pixel offset inside the 128-byte row, 32-byte K-steps.
+// MMA instructions per 128 output pixels drop from 9 to 4.5 (16->16), 7.5 (16->32 s2), 12 from
+// 18 (32->32); stride 2 needs no strided TMA traversal (TF SAME on even sizes: pad 0 before, 1
+// after, supplied by TMA's zero fill, as is the pad 1/1 of stride 1).
+//
+// One tile = 16 output rows x 8 groups (M = 128: TMEM lane = row*8 + group).  One 4-D TMA box
+// load brings the (18 or 33) x (10 or 9) x 128 B patch; weights stay resident in shared memory.
+// Epilogue (4 warps): one tcgen05.ld of all 64 columns, packed FFMA2 scale/shift, F2FP.RELU to
+// 16 bit, swizzled st.shared into a staging tile and ONE TMA store per tile (coalesced, clipped
+// at the image border by the tensor map).
+#pragma once
+#include "tc_common.cuh"
+
+namespace ukbb {
+
+struct ConvGroupParams {
+    int tiles_x, tiles_y, n_tiles;
+    const float* scale;             // [COUT]
+    const float* shift;             // [COUT]
+};
+
+template <int CC, int COUT, int STRIDE>
+struct ConvGroupCfg {
+    static constexpr int G = 64 / CC;                          // input pixels per 128-byte row
+    static constexpr int GOUT = STRIDE == 1 ? G : G / 2;       // output pixels per UMMA row
+    static constexpr int N = GOUT * COUT;
+    static constexpr int J = STRIDE == 1 ? G + 2 : G + 1;      // K-slices per kernel row
+    static constexpr int KS = CC / 16;
+    static constexpr int PU = STRIDE == 1 ? 10 : 9;            // patch groups per row
+    static constexpr int PR = STRIDE == 1 ? 18 : 33;           // patch rows
+    static constexpr int PATCH_TX = PR * PU * 128;
+    static constexpr int PATCH_BYTES = (PATCH_TX + 1023) / 1024 * 1024;
+    static constexpr int B_ROW = CC * 2;
+    static constexpr int B_TILE = (N * B_ROW + 1023) / 1024 * 1024;
+    static constexpr int NB_TILES = 3 * J;
+    static constexpr int B_BYTES = NB_TILES * B_TILE;
+    static constexpr int OUT_BYTES = 128 * 128;                // staging tile [128 rows][128 B]
+    static constexpr int A_MAX = (200 * 1024 - B_BYTES - 2 * OUT_BYTES) / PATCH_BYTES;
+    static constexpr int A_STAGES = A_MAX > 4 ? 4 : A_MAX;
+    static constexpr int ACC_STAGES = 2;
+    static constexpr int TMEM_COLS = 128;
+    static constexpr int SMEM_BYTES = A_STAGES * PATCH_BYTES + B_BYTES + 2 * OUT_BYTES + 1024 + 256 + 2 * N * 4;
+    static_assert(N == 64, "pixel-group kernel is built for N = Gout * Cout = 64");
+    static_assert(STRIDE == 1 || G >= 2, "stride 2 needs at least two pixels per row");
+    static_assert(A_STAGES >= 2, "need at least two patch stages");
+};
+
+namespace tc {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+// (a0, a1) * (b0, b1) + (c0, c1) in one FFMA2, then round both to 16 bit with ReLU (and clamp to
+// the finite FP16 range in FP16 mode): two instructions per pair of outputs.
+template <bool F16>
+__device__ __forceinline__ uint32_t bn_relu_pack(uint32_t a0, uint32_t a1, float2 sc, float2 sh) {
+    uint64_t a, b, c, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(sc.x), "f"(sc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(sh.x), "f"(sh.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
+    uint32_t r;
+    if (F16) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+}  // namespace tc
+
+// static round-robin tile walk without divisions in the loop
+struct TileWalk {
+    int tx, ty, n, dx, dy, dn, tiles_x, tiles_y;
+    __device__ __forceinline__ void init(int first, int step, int tiles_x_, int tiles_y_) {
+        tiles_x = tiles_x_; tiles_y = tiles_y_;
+        tx = first % tiles_x; ty = (first / tiles_x) % tiles_y; n = first / (tiles_x * tiles_y);
+        dx = step % tiles_x; dy = (step / tiles_x) % tiles_y; dn = step / (tiles_x * tiles_y);
+    }
+    __device__ __forceinline__ void next() {
+        tx += dx; if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+        ty += dy; if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+        n += dn;
+    }
+};
+
+template <int CC, int COUT, int STRIDE, bool F16>
+__global__ void __launch_bounds__(256, 1)
+conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_out, const ConvGroupParams p) {
+    using namespace tc;
+    using Cfg = ConvGroupCfg<CC, COUT, STRIDE>;
+    constexpr int AST = Cfg::A_STAGES, G = Cfg::G, J = Cfg::J, KS = Cfg::KS, PU = Cfg::PU, N = Cfg::N;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_base = smem_base + AST * Cfg::PATCH_BYTES;
+    const uint32_t out_base = b_base + Cfg::B_BYTES;
+    const uint32_t bar_base = out_base + 2 * Cfg::OUT_BYTES;
+    // barriers: a_full[AST] a_empty[AST] tfull[2] tempty[2] wfull | tmem slot
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (AST + s); };
+    auto tfull = [&](int a) { return bar_base + 8u * (2 * AST + a); };
+    auto tempty = [&](int a) { return bar_base + 8u * (2 * AST + 2 + a); };
+    const uint32_t wfull = bar_base + 8u * (2 * AST + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * AST + 5);
+    float* s_scale = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [N] expanded (column -> channel)
+    float* s_shift = s_scale + N;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_out); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < AST; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+        mbar_init(wfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+    if (warp == 3) {
+        for (int c = lane; c < N; c += 32) { s_scale[c] = p.scale[c % COUT]; s_shift[c] = p.shift[c % COUT]; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wfull, Cfg::NB_TILES * N * Cfg::B_ROW);
+            for (int t = 0; t < Cfg::NB_TILES; ++t) tma_load_2d(b_base + t * Cfg::B_TILE, &map_b, wfull, 0, t * N);
+            TileWalk w;
+            w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+            int as = 0;
+            uint32_t aph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                mbar_wait(a_empty(as), aph ^ 1);
+                mbar_arrive_expect_tx(a_full(as), Cfg::PATCH_TX);
+                if (STRIDE == 1) tma_load_4d(smem_base + as * Cfg::PATCH_BYTES, &map_a, a_full(as), 0, w.tx * 8 - 1, w.ty * 16 - 1, w.n);
+                else tma_load_4d(smem_base + as * Cfg::PATCH_BYTES, &map_a, a_full(as), 0, w.tx * 8, w.ty * 32, w.n);
+                if (++as == AST) { as = 0; aph ^= 1; }
+                w.next();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+        const bool leader = elect_one();
+        const uint32_t idesc = F16 ? make_idesc_f16(128, N) : make_idesc_bf16(128, N);
+        constexpr uint32_t blayout = Cfg::B_ROW == 128 ? 2u : Cfg::B_ROW == 64 ? 4u : 6u;
+        constexpr uint32_t a_hi = (uint32_t)(((STRIDE == 1 ? PU : 2 * PU) * 128) >> 4) | (1u << 14) | (2u << 29);
+        constexpr uint32_t b_hi = (uint32_t)((8 * Cfg::B_ROW) >> 4) | (1u << 14) | (blayout << 29);
+        const uint32_t b_lo = ((b_base & 0x3FFFF) >> 4) | (1u << 16);
+        mbar_wait(wfull, 0);
+        tc_fence_after();
+        int as = 0, acc = 0;
+        uint32_t aph = 0, acc_ph = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            mbar_wait(tempty(acc), acc_ph ^ 1);
+            mbar_wait(a_full(as), aph);
+            tc_fence_after();
+            const uint32_t d = tmem_base + acc * N;
+            const uint32_t a_lo = (((smem_base + as * Cfg::PATCH_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+            if (leader) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        // input pixel of this K-slice relative to the first pixel of the group: j - 1 (stride 1), j (stride 2)
+                        const int jj = STRIDE == 1 ? j - 1 : j;
+                        const int ro = jj < 0 ? -1 : jj / G;
+                        const int sub = jj - ro * G;
+                        const int arow = STRIDE == 1 ? ky * PU + 1 + ro : ky * PU + ro;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks)
+                            umma_bf16_lohi(d, a_lo + ((arow * 128 + sub * CC * 2 + ks * 32) >> 4), a_hi,
+                                           b_lo + (((ky * J + j) * Cfg::B_TILE + ks * 32) >> 4), b_hi, idesc, (ky | j | ks) != 0 ? 1u : 0u);
+                    }
+                umma_commit(a_empty(as));
+                umma_commit(tfull(acc));
+            }
+            __syncwarp();
+            if (++as == AST) { as = 0; aph ^= 1; }
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;
+        const int r = q * 32 + lane;                         // TMEM lane = tile row * 8 + group
+        const bool issuer = threadIdx.x == 128;
+        TileWalk w;
+        w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            mbar_wait(tfull(acc), acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N;
+            uint32_t v[64];
+            tmem_ld32(taddr, v);
+            tmem_ld32(taddr + 32, v + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));         // accumulator is in registers: release it to the MMA warp
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            uint32_t o[32];
+#pragma unroll
+            for (int c = 0; c < 64; c += 4) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+                const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+                o[c / 2] = bn_relu_pack<F16>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                o[c / 2 + 1] = bn_relu_pack<F16>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+            }
+            // staging set (i & 1) was read by the store of tile i - 2, which the issuer waited for before the last barrier
+            const uint32_t row = out_base + (i & 1) * Cfg::OUT_BYTES + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t dst = row + ((uint32_t)(j ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[4 * j]), "r"(o[4 * j + 1]), "r"(o[4 * j + 2]),
+                             "r"(o[4 * j + 3])
+                             : "memory");
+            }
+            fence_proxy_async();
+            if (issuer) bulk_wait_read<0>();                 // store of tile i - 1 has left its staging set
+            named_bar_sync(1, 128);
+            if (issuer) {
+                tma_store_4d(&map_out, out_base + (i & 1) * Cfg::OUT_BYTES, 0, w.tx * 8, w.ty * 16, w.n);
+                bulk_commit();
+            }
+            w.next();
+        }
+        if (issuer) bulk_wait<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace ukbb

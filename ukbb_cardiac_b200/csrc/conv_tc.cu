@@ -17,6 +17,7 @@
 #include "engine.cuh"
 #include "tc_common.cuh"
 #include "conv_halo.cuh"
+#include "conv_group.cuh"
 #include "head_fused.cuh"
 #include "head_mma.cuh"
 #include <stdlib.h>
@@ -364,14 +365,18 @@ struct TcLayerPlan {
     CUtensorMap map_a, map_b;
     ConvTcParams p;
     ConvHaloParams hp;
+    ConvGroupParams gp;
+    CUtensorMap map_out;
     int cc, cout;
-    int kind = 0;                   // 0 = per-tap implicit GEMM (conv_tc_kernel), 1 = halo reuse (conv_halo_kernel)
+    int kind = 0;                   // 0 = per-tap implicit GEMM (conv_tc_kernel), 1 = halo reuse (conv_halo_kernel),
+                                    // 2 = pixel-group rows (conv_group_kernel)
     bool valid = false;
 };
 
 struct Bf16State {
     EncodeTiledFn encode = nullptr;
     __nv_bfloat16* w[UKBB_N_CONV] = {};      // [cout][taps*cin] bf16, K-major
+    __nv_bfloat16* wg[UKBB_N_CONV] = {};     // pixel-group layers: expanded [3 * J tiles][64 rows][cin] (conv_group.cuh)
     float* w0 = nullptr;                     // conv0_0 weights [9][16] fp32
     __nv_bfloat16* cat = nullptr;            // [nb][h][w][160]
     __nv_bfloat16* f0 = nullptr;             // [nb][h][w][64]
@@ -419,6 +424,41 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     p.n_tiles = p.tiles_x * p.tiles_y * ((nb + bn - 1) / bn);
     P.kind = (ks == 3 && s == 1 && L.cin >= 16 && !getenv("UKBB_NO_HALO")) ? 1 : 0;
+    if (S->wg[li] && wi % (64 / L.cin) == 0 && !getenv("UKBB_NO_GROUP") && !getenv("UKBB_NO_HALO")) P.kind = 2;
+    if (P.kind == 2) {
+        const int g = 64 / L.cin, gout = s == 1 ? g : g / 2;
+        const int pu = s == 1 ? 10 : 9, pr = s == 1 ? 18 : 33, jn = s == 1 ? g + 2 : g + 1;
+        ConvGroupParams& gp = P.gp;
+        gp.tiles_x = (wo / gout + 7) / 8; gp.tiles_y = (ho + 15) / 16; gp.n_tiles = gp.tiles_x * gp.tiles_y * nb;
+        gp.scale = L.scale; gp.shift = L.shift;
+        cuuint32_t e4[4] = {1, 1, 1, 1}, e2[2] = {1, 1};
+        {   // input: rows of g pixels (128 bytes), box = halo patch
+            cuuint64_t dims[4] = {64, (cuuint64_t)(wi / g), (cuuint64_t)hi, (cuuint64_t)nb};
+            cuuint64_t strides[3] = {128, (cuuint64_t)wi * L.cin * 2, (cuuint64_t)hi * wi * L.cin * 2};
+            cuuint32_t box[4] = {64, (cuuint32_t)pu, (cuuint32_t)pr, 1};
+            CUresult r = S->encode(&P.map_a, dt16, 4, (void*)in, dims, strides, box, e4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(group patch, layer %d) failed: %d", li, (int)r); return UKBB_E_CUDA; }
+        }
+        {   // expanded weights: [3 * J tiles * 64 rows][cin]
+            cuuint64_t dims[2] = {(cuuint64_t)L.cin, (cuuint64_t)(3 * jn * 64)};
+            cuuint64_t strides[1] = {(cuuint64_t)L.cin * 2};
+            cuuint32_t box[2] = {(cuuint32_t)L.cin, 64};
+            CUresult r = S->encode(&P.map_b, dt16, 2, (void*)S->wg[li], dims, strides, box, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   swizzle_for(L.cin), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(group weights, layer %d) failed: %d", li, (int)r); return UKBB_E_CUDA; }
+        }
+        {   // output: rows of gout pixels x cout channels = 64 elements, box = 16 rows x 8 groups
+            cuuint64_t dims[4] = {64, (cuuint64_t)(wo / gout), (cuuint64_t)ho, (cuuint64_t)nb};
+            cuuint64_t strides[3] = {128, (cuuint64_t)wo * L.cout * 2, (cuuint64_t)ho * wo * L.cout * 2};
+            cuuint32_t box[4] = {64, 8, 16, 1};
+            CUresult r = S->encode(&P.map_out, dt16, 4, (void*)out, dims, strides, box, e4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(group output, layer %d) failed: %d", li, (int)r); return UKBB_E_CUDA; }
+        }
+        P.valid = true;
+        return UKBB_OK;
+    }
     if (P.kind == 1) {
         ConvHaloParams& hp = P.hp;
         hp.cin = L.cin; hp.chunks = L.cin / cc;
@@ -496,7 +536,34 @@ static int launch_halo(const TcLayerPlan& P, int sms, cudaStream_t st) {
     return P.hp.fp16 ? launch_halo2<CC, COUT, RESIDENT, NKB, true>(P, sms, st) : launch_halo2<CC, COUT, RESIDENT, NKB, false>(P, sms, st);
 }
 
+template <int CC, int COUT, int STRIDE, bool F16>
+static int launch_group2(const TcLayerPlan& P, int sms, cudaStream_t st) {
+    using Cfg = ConvGroupCfg<CC, COUT, STRIDE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(conv_group_kernel<CC, COUT, STRIDE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = P.gp.n_tiles < sms ? P.gp.n_tiles : sms;
+    conv_group_kernel<CC, COUT, STRIDE, F16><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.map_out, P.gp);
+    UKBB_CUDA(cudaGetLastError());
+    return UKBB_OK;
+}
+template <int CC, int COUT, int STRIDE>
+static int launch_group(const TcLayerPlan& P, int sms, cudaStream_t st) {
+    return P.p.fp16 ? launch_group2<CC, COUT, STRIDE, true>(P, sms, st) : launch_group2<CC, COUT, STRIDE, false>(P, sms, st);
+}
+
 static int launch_plan(const TcLayerPlan& P, int sms, cudaStream_t st) {
+    if (P.kind == 2) {
+        if (P.p.cin == 16 && P.cout == 16 && P.p.stride == 1) return launch_group<16, 16, 1>(P, sms, st);
+        if (P.p.cin == 32 && P.cout == 32 && P.p.stride == 1) return launch_group<32, 32, 1>(P, sms, st);
+        if (P.p.cin == 64 && P.cout == 64 && P.p.stride == 1) return launch_group<64, 64, 1>(P, sms, st);
+        if (P.p.cin == 16 && P.cout == 32 && P.p.stride == 2) return launch_group<16, 32, 2>(P, sms, st);
+        if (P.p.cin == 32 && P.cout == 64 && P.p.stride == 2) return launch_group<32, 64, 2>(P, sms, st);
+        set_error("conv_group: no kernel instance for %d -> %d stride %d", P.p.cin, P.cout, P.p.stride);
+        return UKBB_E_UNSUPPORTED;
+    }
     if (P.kind == 1) {
         if (P.cc == 16 && P.cout == 16 && P.hp.chunks == 1) return launch_halo<16, 16, true, 9>(P, sms, st);
         if (P.cc == 32 && P.cout == 32 && P.hp.chunks == 1) return launch_halo<32, 32, true, 9>(P, sms, st);
@@ -570,6 +637,29 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
                     }
         UKBB_CUDA(cudaMalloc(&S->w[i], wb.size() * sizeof(__nv_bfloat16)));
         UKBB_CUDA(cudaMemcpy(S->w[i], wb.data(), wb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        // pixel-group layers (conv_group.cuh): N = gout * cout = 64.  Tile (ky, j) row (s, co) holds tap (ky, kx) with
+        // kx = j - s (stride 1) or j - 2 s (stride 2), zero where that tap does not exist.
+        if (c.ksize == 3 && c.cin <= 64 && 64 % c.cin == 0) {
+            const int g = 64 / c.cin, gout = c.stride == 1 ? g : g / 2;
+            if (gout >= 1 && gout * c.cout == 64) {
+                const int jn = c.stride == 1 ? g + 2 : g + 1;
+                std::vector<__nv_bfloat16> we((size_t)3 * jn * 64 * c.cin);
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int j = 0; j < jn; ++j)
+                        for (int sp = 0; sp < gout; ++sp)
+                            for (int co = 0; co < c.cout; ++co)
+                                for (int ci = 0; ci < c.cin; ++ci) {
+                                    const int kx = c.stride == 1 ? j - sp : j - 2 * sp;
+                                    __nv_bfloat16 v16;
+                                    const uint16_t zero = 0;
+                                    memcpy(&v16, &zero, 2);
+                                    if (kx >= 0 && kx <= 2) v16 = wb[(size_t)co * ktot + (ky * 3 + kx) * c.cin + ci];
+                                    we[((size_t)(ky * jn + j) * 64 + sp * c.cout + co) * c.cin + ci] = v16;
+                                }
+                UKBB_CUDA(cudaMalloc(&S->wg[i], we.size() * sizeof(__nv_bfloat16)));
+                UKBB_CUDA(cudaMemcpy(S->wg[i], we.data(), we.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+            }
+        }
     }
     return UKBB_OK;
 }
@@ -577,7 +667,7 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
 void bf16_release(Engine* h) {
     Bf16State* S = h->tc;
     if (!S) return;
-    for (int i = 0; i < UKBB_N_CONV; ++i) cudaFree(S->w[i]);
+    for (int i = 0; i < UKBB_N_CONV; ++i) { cudaFree(S->w[i]); cudaFree(S->wg[i]); }
     cudaFree(S->w0); cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
     for (int l = 0; l < 5; ++l) { cudaFree(S->t[l]); cudaFree(S->u[l]); }
     cudaFree(S->ones);
@@ -791,6 +881,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             P.p.n_tiles = P.p.tiles_x * P.p.tiles_y * ((nb + P.p.bn - 1) / P.p.bn);
             P.hp.n = nb;
             P.hp.n_tiles = P.hp.tiles_x * P.hp.tiles_y * nb;
+            P.gp.n_tiles = P.gp.tiles_x * P.gp.tiles_y * nb;
             rc = launch_plan(P, h->sms, st);
             if (rc) return rc;
             h->launches++;
