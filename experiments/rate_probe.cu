@@ -104,7 +104,7 @@ static void run_tma(const char* name, void* buf, int C, int W, int H, int nb_tot
 }
 
 // ------------------------------------------------------------------------------------------ MMA rate
-template <int N, int RB>
+template <int N, int RB, bool BMN = false>
 __global__ void __launch_bounds__(128, 1)
 mma_rate_kernel(int sbo_rows, int n_mma, int windows, long long* out) {
     extern __shared__ uint8_t raw[];
@@ -124,7 +124,7 @@ mma_rate_kernel(int sbo_rows, int n_mma, int windows, long long* out) {
     tc_fence_before(); __syncthreads(); tc_fence_after();
     uint32_t tmem; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
     if (threadIdx.x == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, N);
+        constexpr uint32_t idesc = make_idesc_bf16(128, N) | (BMN ? (1u << 16) : 0u);
         constexpr uint32_t layout = RB == 128 ? 2u : RB == 64 ? 4u : 6u;
         const uint32_t a_hi = (uint32_t)((sbo_rows * RB) >> 4) | (1u << 14) | (layout << 29);
         const uint32_t b_hi = (uint32_t)((8 * RB) >> 4) | (1u << 14) | (layout << 29);
@@ -138,7 +138,8 @@ mma_rate_kernel(int sbo_rows, int n_mma, int windows, long long* out) {
                 for (int k = 0; k < RB / 32; ++k) {
                     const int wtap = windows ? tap : 0;
                     umma_bf16_lohi(tmem + (N <= 128 ? ((i / 9) & 1) * N : 0), a_lo + ((((wtap / 3) * 18 + (wtap % 3)) * RB + k * 32) >> 4), a_hi,
-                                   b_lo + (((tap % NBT) * B_TILE + k * 32) >> 4), b_hi, idesc, 1u);
+                                   BMN ? b_lo + (((tap % 4) * 2048) >> 4) : b_lo + (((tap % NBT) * B_TILE + k * 32) >> 4),
+                                   BMN ? ((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29)) : b_hi, idesc, 1u);
                 }
         }
         umma_commit(bar);
@@ -149,23 +150,24 @@ mma_rate_kernel(int sbo_rows, int n_mma, int windows, long long* out) {
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-template <int N, int RB>
+template <int N, int RB, bool BMN = false>
 static void run_mma(int sbo_rows, int windows) {
     long long* dout; CK(cudaMalloc(&dout, 148 * 8));
     const int bt = (N * RB + 1023) / 1024 * 1024;
     const int smem = 48 * 1024 + (9 * bt <= 144 * 1024 ? 9 : (144 * 1024) / bt) * bt + 1024 + 64;
-    CK(cudaFuncSetAttribute(mma_rate_kernel<N, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(mma_rate_kernel<N, RB, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int n_mma = 9 * (RB / 32) * 200;
-    mma_rate_kernel<N, RB><<<148, 128, smem>>>(sbo_rows, n_mma, windows, dout);
+    mma_rate_kernel<N, RB, BMN><<<148, 128, smem>>>(sbo_rows, n_mma, windows, dout);
     CK(cudaDeviceSynchronize());
     long long h[148]; CK(cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost));
     double avg = 0; for (int i = 0; i < 148; ++i) avg += (double)h[i]; avg /= 148;
-    printf("MMA M=128 N=%3d K=16 row %3d B  SBO %2d rows windows=%d : %6.1f cyc/MMA  (floor N/2 = %d)  %5.1f%% of tensor peak\n", N, RB,
+    printf("MMA%s M=128 N=%3d K=16 row %3d B  SBO %2d rows windows=%d : %6.1f cyc/MMA  (floor N/2 = %d)  %5.1f%% of tensor peak\n", BMN ? " B-MN-major" : "", N, RB,
            sbo_rows, windows, avg / n_mma, N / 2, 100.0 * (N / 2.0) / (avg / n_mma));
     cudaFree(dout);
 }
 
 int main(int argc, char** argv) {
+    const bool only_mn = argc > 1;
     void* fn = nullptr; cudaDriverEntryPointQueryResult q;
     CK(cudaFree(0));
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -173,6 +175,11 @@ int main(int argc, char** argv) {
     const int W = 192, H = 208, NB = 128;
     void* buf; CK(cudaMalloc(&buf, (size_t)NB * W * H * 64 * 2));          // up to 64 channels at level-0 size
     CK(cudaMemset(buf, 0, (size_t)NB * W * H * 64 * 2));
+    if (only_mn) {
+        void* fn2 = nullptr; cudaDriverEntryPointQueryResult q2; CK(cudaFree(0));
+        run_mma<64, 128, true>(8, 0); run_mma<64, 64, true>(8, 0); run_mma<64, 32, true>(8, 0); run_mma<64, 128, false>(8, 0); run_mma<64, 64, false>(8, 0);
+        return 0;
+    }
     for (int l2 = 1; l2 >= 0; --l2) {
         run_tma("halo 18x18 C=16 (32 B rows)", buf, 16, W, H, NB, 1, 18, 18, 16, -1, 16, -1, CU_TENSOR_MAP_SWIZZLE_32B, l2);
         run_tma("halo 18x6quad C=16 (128 B rows)", buf, 16, W, H, NB, 4, 6, 18, 4, -1, 16, -1, CU_TENSOR_MAP_SWIZZLE_128B, l2);

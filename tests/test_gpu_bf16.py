@@ -75,7 +75,9 @@ def test_tc_layer(engine, li):
 # 16-bit path: its top-2 logit gap has its mode at 0 (8 % of the pixels have a gap < 0.05 sigma),
 # so a 1 % logit error flips a few per cent of the labels whatever kernel computes it (the CPU
 # emulation experiments/precision_sim.py reproduces the figures below with plain torch ops).
-RANDOM_INIT_FLOOR = {"bf16": (0.97, 0.95), "fp16": (0.996, 0.994)}
+# The head folds the BN scales into the 16-bit weights (a different, equally valid quantisation): on this
+# fixture that moved BF16 from 97.7 % to 98.7 % and FP16 from 99.77 % to 99.64 % (experiments/agree_probe.py).
+RANDOM_INIT_FLOOR = {"bf16": (0.97, 0.95), "fp16": (0.995, 0.99)}
 
 
 @pytest.mark.parametrize("mode", ["bf16", "fp16"])

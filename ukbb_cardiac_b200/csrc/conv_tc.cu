@@ -20,7 +20,9 @@
 #include "conv_group.cuh"
 #include "head_fused.cuh"
 #include "head_mma.cuh"
+#include "head_tc.cuh"
 #include <stdlib.h>
+#include <math.h>
 #include <vector>
 #include <string.h>
 
@@ -384,7 +386,12 @@ struct Bf16State {
     TcLayerPlan plan[UKBB_N_CONV];
     int plan_nb = 0, plan_h = 0, plan_w = 0;
     int fp16 = 0;
-    int fused_head = 2;                      // 0 = unfused, 1 = gather head (head_fused), 2 = tensor-core upsample (head_mma)
+    int fused_head = 3;                      // 0 = unfused, 1 = gather head (head_fused), 2 = tensor-core upsample (head_mma),
+                                             // 3 = head_mma algebra + tensor-core class scores, 4-stage pipeline (head_tc)
+    __nv_bfloat16* wf[UKBB_N_CONV] = {};     // head_tc: weights of same_dim0 / fc0 / fc1 with the BN scale folded in before rounding
+    float h_shift[UKBB_N_CONV][64] = {};     // host copies of the folded-BN shifts of those layers (constant-bank operands)
+    float h_bias[8] = {};
+    float h_wl[64 * 8] = {};                 // class-score weights [k][8] FP32
     CUtensorMap map_s0, map_w0, map_w1;      // fused head operands
     __nv_bfloat16* t[5] = {};                // t_l = W_l . s_l at level l (64 channels), l = 1..4
     __nv_bfloat16* u[5] = {};                // interpolation matrices U_l (16-bit, exact)
@@ -591,7 +598,29 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
     if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return UKBB_E_CUDA; }
     S->encode = (EncodeTiledFn)fn;
     S->fp16 = h->mode == UKBB_MODE_FP16 ? 1 : 0;
-    S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : (getenv("UKBB_HEAD_GATHER") ? 1 : 2);
+    S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : (getenv("UKBB_HEAD_GATHER") ? 1 : (getenv("UKBB_HEAD_V2") ? 2 : 3));
+    {   // class-score layer of head_tc: FP32 weights [k][8] and bias, passed by value (constant bank)
+        const ukbb_conv_weights& c = w->conv[UKBB_N_CONV - 1];
+        for (int k = 0; k < 64; ++k)
+            for (int co = 0; co < 8; ++co) S->h_wl[k * 8 + co] = co < c.cout ? c.kernel[(size_t)k * c.cout + co] : 0.f;
+        for (int co = 0; co < 8; ++co) S->h_bias[co] = co < c.cout ? c.bias[co] : -INFINITY;
+    }
+    for (int li : {13, 18, 19}) {          // 1x1 layers of the head: fold gamma / sqrt(var + eps) into the weights (head_tc.cuh)
+        const ukbb_conv_weights& c = w->conv[li];
+        std::vector<__nv_bfloat16> wb((size_t)c.cout * c.cin);
+        for (int co = 0; co < c.cout; ++co) {
+            const double sc = (double)c.gamma[co] / sqrt((double)c.moving_variance[co] + (double)w->bn_eps);
+            S->h_shift[li][co] = (float)((double)c.beta[co] - (double)c.moving_mean[co] * sc);
+            for (int ci = 0; ci < c.cin; ++ci) {
+                const float v = (float)((double)c.kernel[(size_t)ci * c.cout + co] * sc);
+                __nv_bfloat16& d = wb[(size_t)co * c.cin + ci];
+                if (S->fp16) { const __half hv = __float2half_rn(v); memcpy(&d, &hv, 2); }
+                else d = __float2bfloat16(v);
+            }
+        }
+        UKBB_CUDA(cudaMalloc(&S->wf[li], wb.size() * 2));
+        UKBB_CUDA(cudaMemcpy(S->wf[li], wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+    }
     {   // interpolation matrices of the tensor-core upsample (see head_mma.cuh) and identity scale / zero shift
         std::vector<float> oz(128, 0.f);
         for (int i = 0; i < 64; ++i) oz[i] = 1.f;
@@ -671,6 +700,7 @@ void bf16_release(Engine* h) {
     cudaFree(S->w0); cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
     for (int l = 0; l < 5; ++l) { cudaFree(S->t[l]); cudaFree(S->u[l]); }
     cudaFree(S->ones);
+    for (int i = 0; i < UKBB_N_CONV; ++i) cudaFree(S->wf[i]);
     delete S;
     h->tc = nullptr;
 }
@@ -701,7 +731,7 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
     }
     for (int l = 1; l <= 4; ++l) {
         cudaFree(S->t[l]); S->t[l] = nullptr;
-        if (S->fused_head == 2) UKBB_CUDA(cudaMalloc(&S->t[l], (size_t)nb * (h2 >> l) * (w2 >> l) * 64 * 2));
+        if (S->fused_head >= 2) UKBB_CUDA(cudaMalloc(&S->t[l], (size_t)nb * (h2 >> l) * (w2 >> l) * 64 * 2));
     }
     h->ws.nb = nb; h->ws.h = h2; h->ws.w = w2;
     int li = 0, rc;
@@ -730,7 +760,7 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
         rc = make_plan(h, 19, S->f0, S->f1, nb, h2, w2, 0);
         if (rc) return rc;
     }
-    if (S->fused_head == 2) {
+    if (S->fused_head >= 2) {
         const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         const CUtensorMapSwizzle sw128 = CU_TENSOR_MAP_SWIZZLE_128B;
         cuuint32_t e4[4] = {1, 1, 1, 1}, e2[2] = {1, 1};
@@ -750,7 +780,7 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
             S->tplan[l].p.kofs = 32 * l;
             {   // weight map must span all 160 K columns: rebuild it (make_plan used cin = 32)
                 cuuint64_t d0[2] = {160, 64}; cuuint64_t st0[1] = {320}; cuuint32_t b0[2] = {32, 64};
-                CUresult r = S->encode(&S->tplan[l].map_b, dt16, 2, S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CUresult r = S->encode(&S->tplan[l].map_b, dt16, 2, S->fused_head == 3 ? S->wf[18] : S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(t-layer weights) failed: %d", (int)r); return UKBB_E_CUDA; }
             }
@@ -783,15 +813,15 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         cuuint64_t d0[2] = {160, 64}; cuuint64_t st0[1] = {320}; cuuint32_t b0[2] = {32, 64}; cuuint32_t e2[2] = {1, 1};
         if (r == CUDA_SUCCESS)
-            r = S->encode(&S->map_w0, dt16, 2, S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            r = S->encode(&S->map_w0, dt16, 2, S->fused_head == 3 ? S->wf[18] : S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         cuuint64_t d1[2] = {64, 64}; cuuint64_t st1[1] = {128}; cuuint32_t b1[2] = {64, 64};
         if (r == CUDA_SUCCESS)
-            r = S->encode(&S->map_w1, dt16, 2, S->w[19], d1, st1, b1, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            r = S->encode(&S->map_w1, dt16, 2, S->fused_head == 3 ? S->wf[19] : S->w[19], d1, st1, b1, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(fused head) failed: %d", (int)r); return UKBB_E_CUDA; }
         S->hm.s0 = S->map_s0; S->hm.w0 = S->map_w0; S->hm.w1 = S->map_w1;
-        if (S->fused_head == 2) {
+        if (S->fused_head >= 2) {
             // head_mma computes same_dim0 itself: its level-0 input is the conv0_1 output (16 channels)
             cuuint64_t dimsb[4] = {16, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)nb};
             cuuint64_t stridesb[3] = {32, (cuuint64_t)w2 * 32, (cuuint64_t)h2 * w2 * 32};
@@ -800,7 +830,7 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
                           CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             cuuint64_t dsd[2] = {16, 32}; cuuint64_t ssd[1] = {32}; cuuint32_t bsd[2] = {16, 32};
             if (r == CUDA_SUCCESS)
-                r = S->encode(&S->hm.wsd, dt16, 2, S->w[13], dsd, ssd, bsd, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                r = S->encode(&S->hm.wsd, dt16, 2, S->fused_head == 3 ? S->wf[13] : S->w[13], dsd, ssd, bsd, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(head same_dim0) failed: %d", (int)r); return UKBB_E_CUDA; }
         }
@@ -833,8 +863,21 @@ static int launch_head_mma2(const Bf16State* S, const HeadParams& hp, int sms, c
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
 }
+template <int NC, bool F16>
+static int launch_head_tc2(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(head_tc_kernel<NC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_SMEM));
+        attr_set = true;
+    }
+    const int grid = hp.n_tiles < sms ? hp.n_tiles : sms;
+    head_tc_kernel<NC, F16><<<grid, H3_THREADS, H3_SMEM, st>>>(S->hm, hp);
+    UKBB_CUDA(cudaGetLastError());
+    return UKBB_OK;
+}
 template <int NC>
 static int launch_head(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+    if (S->fused_head == 3) return S->fp16 ? launch_head_tc2<NC, true>(S, hp, sms, st) : launch_head_tc2<NC, false>(S, hp, sms, st);
     if (S->fused_head == 2) return S->fp16 ? launch_head_mma2<NC, true>(S, hp, sms, st) : launch_head_mma2<NC, false>(S, hp, sms, st);
     return S->fp16 ? launch_head2<NC, true>(S, hp, sms, st) : launch_head2<NC, false>(S, hp, sms, st);
 }
@@ -875,7 +918,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             h->launches++;
         }
         for (int li = 1; li < 18; ++li) {
-            if (li == 13 && S->fused_head == 2) continue;        // same_dim0 lives inside head_mma_kernel
+            if (li == 13 && S->fused_head >= 2) continue;        // same_dim0 lives inside head_mma_kernel
             TcLayerPlan P = S->plan[li];
             P.p.n = nb;
             P.p.n_tiles = P.p.tiles_x * P.p.tiles_y * ((nb + P.p.bn - 1) / P.p.bn);
@@ -886,7 +929,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             if (rc) return rc;
             h->launches++;
         }
-        if (S->fused_head == 2) {
+        if (S->fused_head >= 2) {
             for (int l = 1; l <= 4; ++l) {
                 TcLayerPlan P = S->tplan[l];
                 P.p.n = nb;
@@ -907,6 +950,12 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             hp.scale1 = h->layers[19].scale; hp.shift1 = h->layers[19].shift;
             hp.scale_sd0 = h->layers[13].scale; hp.shift_sd0 = h->layers[13].shift;
             hp.wlog = h->layers[20].w_f32; hp.blog = h->layers[20].shift;
+            memcpy(hp.c_shift_sd0, S->h_shift[13], sizeof(hp.c_shift_sd0));
+            memcpy(hp.c_shift0, S->h_shift[18], sizeof(hp.c_shift0));
+            memcpy(hp.c_shift1, S->h_shift[19], sizeof(hp.c_shift1));
+            memcpy(hp.c_bias, S->h_bias, sizeof(hp.c_bias));
+            for (int k2 = 0; k2 < 32; ++k2)
+                for (int c = 0; c < 8; ++c) hp.c_wl2[k2][c] = make_float2(S->h_wl[(2 * k2) * 8 + c], S->h_wl[(2 * k2 + 1) * 8 + c]);
             const size_t po = (size_t)n0 * h2 * w2 * h->n_class;
             hp.labels = labels + (size_t)n0 * x * y;
             hp.logits = logits ? logits + po : nullptr;

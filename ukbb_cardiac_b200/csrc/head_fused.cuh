@@ -38,6 +38,10 @@ struct HeadParams {
     float* logits;                  // optional [n][h][w][nc]
     float* prob;                    // optional
     unsigned long long* counts;     // optional [n][nc]
+    // head_tc only: BN scales are folded into the 16-bit weights, the shifts travel by value so that the
+    // epilogues read them as constant-bank operands (no shared-memory loads, no registers)
+    float c_shift_sd0[32], c_shift0[64], c_shift1[64], c_bias[8];
+    float2 c_wl2[32][8];            // class-score weights FP32 as input-channel pairs: [k / 2][class] = (w[k][c], w[k + 1][c])
 };
 
 constexpr int HEAD_THREADS = 448;

@@ -39,20 +39,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded wait: a lost TMA transaction or a descriptor fault must not hang the GPU (the box is
-// shared); after 2^24 failed probes (seconds) the kernel traps and the launch returns an error.
+// shared); after 2^22 failed probes (each sleeps up to 20 us in hardware) the kernel traps and the launch returns an error.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
         asm volatile(
             "{\n"
             ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, P1;\n"
             "}\n"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)     // suspend-time hint (ns): sleep in hardware instead of re-issuing the probe
             : "memory");
-        if (!done && spins > (1u << 24)) __trap();
+        if (!done && spins > (1u << 22)) __trap();
     }
 }
 
