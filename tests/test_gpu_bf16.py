@@ -152,3 +152,26 @@ def test_fused_and_unfused_paths_agree(monkeypatch):
         rel = float((g - g2).abs().max() / g2.abs().max())
         assert rel < 5e-3, (name, rel)
         assert float((l == l2).float().mean()) >= 0.998, name
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(3, 64, 96), (5, 48, 80), (130, 32, 48)])
+def test_side_kernel_bit_identical(monkeypatch, mode, shape):
+    """side_tc_kernel (same_dim_l + fc0 column block of levels 1..4 chained in one launch, s_l kept
+    on chip) rounds at the same two points as the two conv_tc launches per level it replaces, so
+    logits and labels are bit-identical -- including partial last tiles (72 or 30 pixels at level 4)."""
+    w = synth.make_weights(0, 4)
+    img = np.random.default_rng(shape[0]).random(shape + (1,)).astype(np.float32)
+    dev = to_device_layout(img)
+    with FCNEngine(w, mode=mode) as eng:
+        l1, g1, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+        n_side = eng.launch_count
+    monkeypatch.setenv("UKBB_NO_SIDE", "1")
+    with FCNEngine(w, mode=mode) as eng:
+        l2, g2, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+        n_plain = eng.launch_count
+    assert n_plain - n_side == 7 * ((shape[0] + 127) // 128)        # 8 launches became 1 per sub-batch
+    assert torch.equal(g1, g2)
+    assert torch.equal(l1, l2)

@@ -21,6 +21,7 @@
 #include "head_fused.cuh"
 #include "head_mma.cuh"
 #include "head_tc.cuh"
+#include "side_tc.cuh"
 #include <stdlib.h>
 #include <math.h>
 #include <vector>
@@ -398,6 +399,8 @@ struct Bf16State {
     float* ones = nullptr;                   // [64] ones then [64] zeros
     TcLayerPlan tplan[5];
     HeadMmaMaps hm;
+    SideMaps sm;                             // side_tc_kernel: same_dim_l + fc0 column block of levels 1..4 in one launch
+    int side = 1;
 };
 
 static CUtensorMapSwizzle swizzle_for(int cc) {
@@ -599,6 +602,7 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
     S->encode = (EncodeTiledFn)fn;
     S->fp16 = h->mode == UKBB_MODE_FP16 ? 1 : 0;
     S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : (getenv("UKBB_HEAD_GATHER") ? 1 : (getenv("UKBB_HEAD_V2") ? 2 : 3));
+    S->side = (S->fused_head == 3 && !getenv("UKBB_NO_SIDE")) ? 1 : 0;
     {   // class-score layer of head_tc: FP32 weights [k][8] and bias, passed by value (constant bank)
         const ukbb_conv_weights& c = w->conv[UKBB_N_CONV - 1];
         for (int k = 0; k < 64; ++k)
@@ -803,6 +807,32 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
             }
         }
     }
+    if (S->side) {
+        const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        cuuint32_t e2[2] = {1, 1};
+        CUresult r = CUDA_SUCCESS;
+        for (int l = 1; l <= 4 && r == CUDA_SUCCESS; ++l) {
+            const int cin = kNFilterTc[l], kc = cin < 64 ? cin : 64;
+            const cuuint64_t rows = (cuuint64_t)nb * (h2 >> l) * (w2 >> l);
+            const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+            cuuint64_t di[2] = {(cuuint64_t)cin, rows}; cuuint64_t si[1] = {(cuuint64_t)cin * 2}; cuuint32_t bi[2] = {(cuuint32_t)kc, 128};
+            r = S->encode(&S->sm.in[l - 1], dt16, 2, (void*)level_out[l], di, si, bi, e2, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            cuuint64_t dout[2] = {64, rows}; cuuint64_t so[1] = {128}; cuuint32_t bo[2] = {64, 128};
+            if (r == CUDA_SUCCESS)
+                r = S->encode(&S->sm.out[l - 1], dt16, 2, S->t[l], dout, so, bo, e2, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            cuuint64_t dw[2] = {(cuuint64_t)cin, 32}; cuuint64_t sw1[1] = {(cuuint64_t)cin * 2}; cuuint32_t bw2[2] = {(cuuint32_t)kc, 32};
+            if (r == CUDA_SUCCESS)
+                r = S->encode(&S->sm.wsd[l - 1], dt16, 2, S->w[13 + l], dw, sw1, bw2, e2, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        cuuint64_t d0[2] = {160, 64}; cuuint64_t st0[1] = {320}; cuuint32_t b0[2] = {32, 64};
+        if (r == CUDA_SUCCESS)
+            r = S->encode(&S->sm.w0, dt16, 2, S->wf[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(side branches) failed: %d", (int)r); return UKBB_E_CUDA; }
+    }
     {   // fused head operands: s0 tiles (8 rows x 16 columns x 32 channels), fc0 / fc1 weights
         const CUtensorMapDataType dt16 = S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         cuuint64_t dims[4] = {32, (cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)nb};
@@ -875,6 +905,19 @@ static int launch_head_tc2(const Bf16State* S, const HeadParams& hp, int sms, cu
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
 }
+template <bool F16>
+static int launch_side(const Bf16State* S, const SideParams& sp, int sms, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(side_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_SMEM));
+        attr_set = true;
+    }
+    const int n_tiles = sp.tile_start[4];
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    side_tc_kernel<F16><<<grid, SD_THREADS, SD_SMEM, st>>>(S->sm, sp);
+    UKBB_CUDA(cudaGetLastError());
+    return UKBB_OK;
+}
 template <int NC>
 static int launch_head(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
     if (S->fused_head == 3) return S->fp16 ? launch_head_tc2<NC, true>(S, hp, sms, st) : launch_head_tc2<NC, false>(S, hp, sms, st);
@@ -919,6 +962,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
         }
         for (int li = 1; li < 18; ++li) {
             if (li == 13 && S->fused_head >= 2) continue;        // same_dim0 lives inside head_mma_kernel
+            if (li > 13 && S->side) break;                       // same_dim 1..4 live inside side_tc_kernel
             TcLayerPlan P = S->plan[li];
             P.p.n = nb;
             P.p.n_tiles = P.p.tiles_x * P.p.tiles_y * ((nb + P.p.bn - 1) / P.p.bn);
@@ -929,7 +973,20 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             if (rc) return rc;
             h->launches++;
         }
-        if (S->fused_head >= 2) {
+        if (S->side) {
+            SideParams sp;
+            int acc_tiles = 0;
+            for (int k = 0; k < 4; ++k) {
+                const int l = 4 - k;
+                sp.tile_start[k] = acc_tiles;
+                acc_tiles += (int)(((long long)nb * (h2 >> l) * (w2 >> l) + 127) / 128);
+                sp.scale[l - 1] = h->layers[13 + l].scale; sp.shift[l - 1] = h->layers[13 + l].shift;
+            }
+            sp.tile_start[4] = acc_tiles;
+            rc = S->fp16 ? launch_side<true>(S, sp, h->sms, st) : launch_side<false>(S, sp, h->sms, st);
+            if (rc) return rc;
+            h->launches++;
+        } else if (S->fused_head >= 2) {
             for (int l = 1; l <= 4; ++l) {
                 TcLayerPlan P = S->tplan[l];
                 P.p.n = nb;
