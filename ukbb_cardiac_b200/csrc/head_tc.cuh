@@ -125,6 +125,9 @@ head_tc_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
 
     if (warp == 12) {
         // ===================== TMA producer =====================
+        // The five box loads of a tile (b0 tile + four t_l patches) are ONE warp instruction: lane l < 5 loads level l with
+        // its own tensor map / destination / coordinates (measured: a tensor load costs its issuing thread ~330 cycles
+        // whatever the box size, profiles/r1_rate_probe.log, so five back-to-back loads from one lane bound the tile period).
         if (lane == 0) {
             mbar_arrive_expect_tx(BAR(WFULL), HM_U_BYTES + HM_W0 + HM_W1 + HM_WSD);
             tma_load_2d(wsd_base, &maps.wsd, BAR(WFULL), 0, 0);
@@ -135,26 +138,28 @@ head_tc_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             tma_load_2d(u_base + HM_U1 + HM_U2 + HM_U3 + 128 * 32, &maps.u4, BAR(WFULL), 0, 128);
             tma_load_2d(w0_base, &maps.w0, BAR(WFULL), 0, 0);
             tma_load_2d(w1_base, &maps.w1, BAR(WFULL), 0, 0);
-            TileWalk w;
-            w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
-            int s3 = 0;
-            uint32_t ph = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                const int y0 = w.ty * 8, x0 = w.tx * 16, n = w.n;
-                mbar_wait(BAR(IN_EMPTY + s3), ph ^ 1);
-                const uint32_t dst = in_base + s3 * HM_IN_BYTES;
-                const uint32_t fullb = BAR(IN_FULL + s3);
-                mbar_arrive_expect_tx(fullb, HM_IN_TX);
-                tma_load_4d(dst, &maps.s0, fullb, 0, x0, y0, n);
-                // level l patch origin: ((x0 + pb) >> l) - 1, pb = (2^l - 1) / 2
-                tma_load_4d(dst + HM_IN_S0, &maps.t1, fullb, 0, (x0 >> 1) - 1, (y0 >> 1) - 1, n);
-                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1, &maps.t2, fullb, 0, ((x0 + 1) >> 2) - 1, ((y0 + 1) >> 2) - 1, n);
-                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1 + HM_IN_P2, &maps.t3, fullb, 0, ((x0 + 3) >> 3) - 1, ((y0 + 3) >> 3) - 1, n);
-                tma_load_4d(dst + HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3, &maps.t4, fullb, 0, ((x0 + 7) >> 4) - 1,
-                            ((y0 + 7) >> 4) - 1, n);
-                if (++s3 == H3_STAGES) { s3 = 0; ph ^= 1; }
-                w.next();
-            }
+        }
+        __syncwarp();
+        TileWalk w;
+        w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+        const int l = lane < 5 ? lane : 0;
+        const CUtensorMap* my_map = &maps.s0 + l;                                   // s0, t1, t2, t3, t4 are adjacent
+        const uint32_t my_off = l == 0 ? 0u : l == 1 ? (uint32_t)HM_IN_S0 : l == 2 ? (uint32_t)(HM_IN_S0 + HM_IN_P1)
+                                : l == 3 ? (uint32_t)(HM_IN_S0 + HM_IN_P1 + HM_IN_P2) : (uint32_t)(HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3);
+        const int pb = ((1 << l) - 1) >> 1, back = l > 0 ? 1 : 0;                   // level l patch origin: ((x0 + pb) >> l) - 1
+        int s3 = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int y0 = w.ty * 8, x0 = w.tx * 16, n = w.n;
+            mbar_wait(BAR(IN_EMPTY + s3), ph ^ 1);
+            const uint32_t dst = in_base + s3 * HM_IN_BYTES;
+            const uint32_t fullb = BAR(IN_FULL + s3);
+            if (lane == 0) mbar_arrive_expect_tx(fullb, HM_IN_TX);
+            __syncwarp();
+            if (lane < 5) tma_load_4d(dst + my_off, my_map, fullb, 0, ((x0 + pb) >> l) - back, ((y0 + pb) >> l) - back, n);
+            __syncwarp();
+            if (++s3 == H3_STAGES) { s3 = 0; ph ^= 1; }
+            w.next();
         }
     } else if (warp == 13) {
         // ===================== MMA issuer 0: same_dim0 (S0) =====================
@@ -238,10 +243,40 @@ head_tc_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             __syncwarp();
         }
     } else if (warp < 4) {
-        // ===================== E0 (D0 -> A0, one tile ahead) and E1 (D1 -> A2), warps 0-3 =====================
+        // ===================== E0 (D0 -> A0, two tiles ahead) and E1 (D1 -> A2), warps 0-3 =====================
         const int q = warp;
         const int r = q * 32 + lane;
-        for (int it = 0; it <= my_tiles; ++it) {
+        // E1 trails E0 by TWO tiles: S1(i) (9 UMMAs) is issued at the end of iteration i and its accumulator is first
+        // needed in iteration i + 2, so this warp never sits waiting for the tensor pipe between its two roles.
+        for (int it = 0; it <= my_tiles + 1; ++it) {
+            if (it >= 2) {
+                const int i = it - 2, b = i & 1;
+                const uint32_t ph = ((uint32_t)i >> 1) & 1u;
+                mbar_wait(BAR(A2_EMPTY + b), ph ^ 1);              // satisfied long before the accumulator is: off the critical path
+                mbar_wait(BAR(D1_FULL + b), ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + H3_D1 + b * 64;
+                uint32_t v[64];
+                tmem_ld32(taddr, v);
+                tmem_ld32(taddr + 32, v + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(A0_FULL + b));       // D1[b] drained: half of the arrivals S1(i + 2) waits for
+                const uint32_t row = a2_base + b * HM_A2 + r * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) o[u] = add_relu_pack<F16>(v[8 * j + 2 * u], v[8 * j + 2 * u + 1], p.c_shift0[8 * j + 2 * u],
+                                                                          p.c_shift0[8 * j + 2 * u + 1]);
+                    const uint32_t dst = row + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
+            }
             if (it < my_tiles) {
                 const int i = it, b = i & 1, s3 = i % H3_STAGES;
                 const uint32_t ph = ((uint32_t)i >> 1) & 1u;
@@ -269,34 +304,6 @@ head_tc_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(A0_FULL + b));
             }
-            if (it >= 1) {
-                const int i = it - 1, b = i & 1;
-                const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-                mbar_wait(BAR(A2_EMPTY + b), ph ^ 1);              // satisfied long before the accumulator is: off the critical path
-                mbar_wait(BAR(D1_FULL + b), ph);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + H3_D1 + b * 64;
-                uint32_t v[64];
-                tmem_ld32(taddr, v);
-                tmem_ld32(taddr + 32, v + 32);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(A0_FULL + b));       // D1[b] drained: half of the arrivals S1(i + 2) waits for
-                const uint32_t row = a2_base + b * HM_A2 + r * 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) o[u] = add_relu_pack<F16>(v[8 * j + 2 * u], v[8 * j + 2 * u + 1], p.c_shift0[8 * j + 2 * u],
-                                                                          p.c_shift0[8 * j + 2 * u + 1]);
-                    const uint32_t dst = row + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
-            }
         }
     } else if (warp < 12) {
         // ===================== E2: FP32 class scores -> labels; warps 4-7 even tiles, warps 8-11 odd tiles =====================
@@ -318,36 +325,18 @@ head_tc_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(A2_FULL + b));           // D2[b] drained: half of the arrivals S2(i + 2) waits for
-            // class scores in FP32: two input channels per FFMA2 (even / odd partial sums); weights and shifts are
-            // broadcast shared-memory loads (uniform-register operands spill: 63 URs per warp)
-            uint64_t acc[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) asm("mov.b64 %0, {%1, %2};" : "=l"(acc[c]) : "f"(p.c_bias[c]), "f"(0.f));    // -inf for c >= n_class
-#pragma unroll
-            for (int k2 = 0; k2 < 32; ++k2) {
-                uint64_t a, sh, d, f;
-                const float2 shv = s_sh2[k2];
-                asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(v[2 * k2]), "r"(v[2 * k2 + 1]));
-                asm("mov.b64 %0, {%1, %2};" : "=l"(sh) : "f"(shv.x), "f"(shv.y));
-                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(sh));
-                float f0, f1;
-                asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(d));
-                f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f);
-                asm("mov.b64 %0, {%1, %2};" : "=l"(f) : "f"(f0), "f"(f1));
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const float2 wv = s_wl2[k2 * 8 + c];
-                    uint64_t wp;
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(wp) : "f"(wv.x), "f"(wv.y));
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[c]) : "l"(f), "l"(wp));
-                }
-            }
+            // class scores in FP32 on plain FFMAs whose second operand is a CONSTANT-BANK word (the weights, shifts and
+            // bias travel by value in the kernel parameters): no shared-memory loads and no register-pair packing moves --
+            // the head is bound by shared-memory bandwidth (UMMA operand reads + epilogue stores + TMA writes), so the
+            // epilogue must not add broadcast LDS traffic of its own.
             float lg[NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                float lo, hi;
-                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[c]));
-                lg[c] = lo + hi;
+            for (int c = 0; c < NC; ++c) lg[c] = p.c_bias[c];                                   // -inf for c >= n_class
+#pragma unroll
+            for (int k = 0; k < 64; ++k) {
+                const float f = fmaxf(__uint_as_float(v[k]) + p.c_shift1[k], 0.f);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) lg[c] = fmaf(f, (k & 1) ? p.c_wl2[k >> 1][c].y : p.c_wl2[k >> 1][c].x, lg[c]);
             }
             const int n = w.n, y = w.ty * 8 + ty, x = w.tx * 16 + tx;
             float m1 = lg[0], m2 = -INFINITY;
