@@ -9,7 +9,7 @@ for row in csv.DictReader(lines):
     if unit=='ns': val/=1e3
     elif unit=='ms': val*=1e3
     seq.append((re.sub(r'\(.*','',row['Kernel Name']).replace('void ','').replace('ukbb::',''),val))
-first=[i for i,(k,v) in enumerate(seq) if k.startswith('conv0')]
+first=[i for i,(k,v) in enumerate(seq) if k.startswith('conv0') or k.startswith('conv_first')]
 a=first[0]; b=first[1] if len(first)>1 else len(seq)
 print('--- one sub-batch ---')
 for k,v in seq[a:b]: print(f'{k[:58]:58s} {v:9.1f} us')

@@ -24,6 +24,11 @@ pytestmark = pytest.mark.gpu
 TDT = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
 
+def SUB_BATCHES(n, cap=500):
+    """forward_bf16 splits n slices into ceil(n / 500) equal sub-batches (conv_tc.cu)."""
+    return -(-n // cap)
+
+
 def bf16_round(a: np.ndarray, dt=torch.bfloat16) -> np.ndarray:
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dt).to(torch.float32).numpy()
 
@@ -155,7 +160,7 @@ def test_fused_and_unfused_paths_agree(monkeypatch):
 
 
 @pytest.mark.parametrize("mode", ["bf16", "fp16"])
-@pytest.mark.parametrize("shape", [(3, 64, 96), (5, 48, 80), (130, 32, 48)])
+@pytest.mark.parametrize("shape", [(3, 64, 96), (5, 48, 80), (130, 32, 48), (510, 32, 32)])
 def test_side_kernel_bit_identical(monkeypatch, mode, shape):
     """side_tc_kernel (same_dim_l + fc0 column block of levels 1..4 chained in one launch, s_l kept
     on chip) rounds at the same two points as the two conv_tc launches per level it replaces, so
@@ -172,6 +177,30 @@ def test_side_kernel_bit_identical(monkeypatch, mode, shape):
         l2, g2, _ = eng.forward(dev, want_logits=True)
         torch.cuda.synchronize()
         n_plain = eng.launch_count
-    assert n_plain - n_side == 7 * ((shape[0] + 127) // 128)        # 8 launches became 1 per sub-batch
+    assert n_plain - n_side == 7 * SUB_BATCHES(shape[0])            # 8 launches became 1 per sub-batch
+    assert torch.equal(g1, g2)
+    assert torch.equal(l1, l2)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(3, 64, 96), (5, 48, 80), (2, 208, 192), (130, 32, 48), (501, 16, 32)])
+def test_first_kernel_bit_identical(monkeypatch, mode, shape):
+    """conv_first_kernel (conv0_0 on the CUDA cores building the halo patch of conv0_1 in shared
+    memory, a0 never written to HBM) does the same FP32 FMA sequence and the same UMMAs as the two
+    launches it replaces: logits and labels are bit-identical, including partial border tiles and
+    the zero padding of a0 (not of the image) around the picture."""
+    w = synth.make_weights(0, 4)
+    img = np.random.default_rng(shape[1]).random(shape + (1,)).astype(np.float32)
+    dev = to_device_layout(img)
+    with FCNEngine(w, mode=mode) as eng:
+        l1, g1, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+        n_first = eng.launch_count
+    monkeypatch.setenv("UKBB_NO_FIRST", "1")
+    with FCNEngine(w, mode=mode) as eng:
+        l2, g2, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+        n_plain = eng.launch_count
+    assert n_plain - n_first == SUB_BATCHES(shape[0])                   # 2 launches became 1 per sub-batch
     assert torch.equal(g1, g2)
     assert torch.equal(l1, l2)

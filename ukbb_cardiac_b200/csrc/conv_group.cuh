@@ -121,6 +121,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     using namespace tc;
     using Cfg = ConvGroupCfg<CC, COUT, STRIDE>;
     constexpr int AST = Cfg::A_STAGES, G = Cfg::G, J = Cfg::J, KS = Cfg::KS, PU = Cfg::PU, N = Cfg::N;
+    griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_base = smem_base + AST * Cfg::PATCH_BYTES;
@@ -154,6 +155,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp != 0) griddep_wait();                       // the producer waits after it has issued the weight loads
     const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (warp == 0) {
@@ -161,6 +163,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (lane == 0) {
             mbar_arrive_expect_tx(wfull, Cfg::NB_TILES * N * Cfg::B_ROW);
             for (int t = 0; t < Cfg::NB_TILES; ++t) tma_load_2d(b_base + t * Cfg::B_TILE, &map_b, wfull, 0, t * N);
+            griddep_wait();
             TileWalk w;
             w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
             int as = 0;

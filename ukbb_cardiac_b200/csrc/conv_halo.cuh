@@ -53,6 +53,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     using namespace tc;
     using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB>;
     constexpr int RB = Cfg::RB, AST = Cfg::A_STAGES, BST = Cfg::B_TILES, ACC = Cfg::ACC_STAGES;
+    griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_base = smem_base + AST * Cfg::PATCH_BYTES;
@@ -90,6 +91,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp != 0) griddep_wait();                       // the producer waits after it has issued the weight loads
     const int tiles_per_slice = p.tiles_x * p.tiles_y;
 
     if (warp == 0) {
@@ -102,6 +104,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tma_load_2d(b_base + kb * Cfg::B_TILE, &map_b, wfull, tap * p.cin + ch * CC, 0);
                 }
             }
+            griddep_wait();
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {

@@ -18,6 +18,7 @@
 #include "tc_common.cuh"
 #include "conv_halo.cuh"
 #include "conv_group.cuh"
+#include "conv_first.cuh"
 #include "head_fused.cuh"
 #include "head_mma.cuh"
 #include "head_tc.cuh"
@@ -63,6 +64,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const ConvTcParams p) {
     using Cfg = ConvTcCfg<CC, COUT>;
     constexpr int STAGES = Cfg::STAGES;
+    griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
@@ -95,10 +97,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp != 0) griddep_wait();                       // the producer waits after it has issued the weight loads
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            griddep_wait();
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -201,38 +205,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
-// conv0_0 (Cin = 1, K = 9): FP32 image in, BF16 NHWC out, CUDA cores (11.5 MFLOP / slice; the
+// conv0_0 (Cin = 1, K = 9): FP32 image in, 16-bit NHWC out, CUDA cores (11.5 MFLOP / slice; the
 // kernel is bound by its 1.3 MB / slice output write).  One thread = one pixel x 16 channels.
+// The 144 weights (BN scale folded in, FP32) and the 16 shifts travel BY VALUE in the kernel
+// parameters, so every FFMA takes its weight as a constant-bank operand: the first version read
+// them from shared memory (144 broadcast LDS per pixel) and ran at a third of the HBM write rate.
 // ------------------------------------------------------------------------------------------
+struct Conv0Params {
+    float w[9][16];                 // [tap = dy * 3 + dx][cout], scale folded in
+    float shift[16];
+};
+
+template <bool F16>
 __global__ void __launch_bounds__(256)
-conv0_bf16_kernel(const float* __restrict__ img, const float* __restrict__ wt /*[9][16]*/,
-                  const float* __restrict__ scale, const float* __restrict__ shift,
-                  __nv_bfloat16* __restrict__ out, long long total, int h, int w, int fp16) {
-    __shared__ float s_w[9 * 16], s_sc[16], s_sh[16];
-    if (threadIdx.x < 144) s_w[threadIdx.x] = wt[threadIdx.x];
-    if (threadIdx.x < 16) { s_sc[threadIdx.x] = scale[threadIdx.x]; s_sh[threadIdx.x] = shift[threadIdx.x]; }
-    __syncthreads();
+conv0_bf16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long long total, int h, int w,
+                  const __grid_constant__ Conv0Params cp) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int x = (int)(idx % w), y = (int)((idx / w) % h);
-    const float* base = img + (idx - (long long)y * w - x);
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    const float* base = img + idx;
+    float v[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
             const int yy = y + ky - 1, xx = x + kx - 1;
-            const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(base + (long long)yy * w + xx) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, s_w[(ky * 3 + kx) * 16 + j], acc[j]);
+            v[ky * 3 + kx] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(base + (ky - 1) * w + (kx - 1)) : 0.f;
         }
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = cp.shift[j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(v[t], cp.w[t][j], acc[j]);
     uint32_t o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        o[j] = pack16(fmaxf(fmaf(acc[2 * j], s_sc[2 * j], s_sh[2 * j]), 0.f),
-                      fmaxf(fmaf(acc[2 * j + 1], s_sc[2 * j + 1], s_sh[2 * j + 1]), 0.f), fp16);
+    for (int j = 0; j < 8; ++j) {
+        if (F16) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(o[j]) : "f"(acc[2 * j + 1]), "f"(acc[2 * j]));
+        else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o[j]) : "f"(acc[2 * j + 1]), "f"(acc[2 * j]));
+    }
     uint4* d4 = reinterpret_cast<uint4*>(out + idx * 16);
     d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
     d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -380,7 +392,7 @@ struct Bf16State {
     EncodeTiledFn encode = nullptr;
     __nv_bfloat16* w[UKBB_N_CONV] = {};      // [cout][taps*cin] bf16, K-major
     __nv_bfloat16* wg[UKBB_N_CONV] = {};     // pixel-group layers: expanded [3 * J tiles][64 rows][cin] (conv_group.cuh)
-    float* w0 = nullptr;                     // conv0_0 weights [9][16] fp32
+    Conv0Params c0;                          // conv0_0: FP32 weights with the BN scale folded in + shifts (kernel parameters)
     __nv_bfloat16* cat = nullptr;            // [nb][h][w][160]
     __nv_bfloat16* f0 = nullptr;             // [nb][h][w][64]
     __nv_bfloat16* f1 = nullptr;
@@ -401,6 +413,7 @@ struct Bf16State {
     HeadMmaMaps hm;
     SideMaps sm;                             // side_tc_kernel: same_dim_l + fc0 column block of levels 1..4 in one launch
     int side = 1;
+    int first = 1;                           // conv0_0 + conv0_1 in one launch (conv_first.cuh)
 };
 
 static CUtensorMapSwizzle swizzle_for(int cc) {
@@ -509,6 +522,21 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     return UKBB_OK;
 }
 
+// Launch with programmatic stream serialization (tc_common.cuh: griddep_launch / griddep_wait): the next kernel's
+// CTAs start their prologue on an SM as soon as the previous kernel's CTA there has exited, instead of after the
+// whole grid has drained.  UKBB_NO_PDL=1 falls back to plain stream order.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool pdl = getenv("UKBB_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int CC, int COUT, bool F16>
 static int launch_tc2(const TcLayerPlan& P, int sms, cudaStream_t st) {
     using Cfg = ConvTcCfg<CC, COUT>;
@@ -518,8 +546,7 @@ static int launch_tc2(const TcLayerPlan& P, int sms, cudaStream_t st) {
         attr_set = true;
     }
     const int grid = P.p.n_tiles < sms ? P.p.n_tiles : sms;
-    conv_tc_kernel<CC, COUT, F16><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.p);
-    UKBB_CUDA(cudaGetLastError());
+    UKBB_CUDA(launch_pdl(conv_tc_kernel<CC, COUT, F16>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.p));
     return UKBB_OK;
 }
 template <int CC, int COUT>
@@ -537,8 +564,7 @@ static int launch_halo2(const TcLayerPlan& P, int sms, cudaStream_t st) {
         attr_set = true;
     }
     const int grid = P.hp.n_tiles < sms ? P.hp.n_tiles : sms;
-    conv_halo_kernel<CC, COUT, RESIDENT, NKB, F16><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.hp);
-    UKBB_CUDA(cudaGetLastError());
+    UKBB_CUDA(launch_pdl(conv_halo_kernel<CC, COUT, RESIDENT, NKB, F16>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.hp));
     return UKBB_OK;
 }
 template <int CC, int COUT, bool RESIDENT, int NKB>
@@ -555,8 +581,7 @@ static int launch_group2(const TcLayerPlan& P, int sms, cudaStream_t st) {
         attr_set = true;
     }
     const int grid = P.gp.n_tiles < sms ? P.gp.n_tiles : sms;
-    conv_group_kernel<CC, COUT, STRIDE, F16><<<grid, 256, Cfg::SMEM_BYTES, st>>>(P.map_a, P.map_b, P.map_out, P.gp);
-    UKBB_CUDA(cudaGetLastError());
+    UKBB_CUDA(launch_pdl(conv_group_kernel<CC, COUT, STRIDE, F16>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.map_out, P.gp));
     return UKBB_OK;
 }
 template <int CC, int COUT, int STRIDE>
@@ -603,11 +628,21 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
     S->fp16 = h->mode == UKBB_MODE_FP16 ? 1 : 0;
     S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : (getenv("UKBB_HEAD_GATHER") ? 1 : (getenv("UKBB_HEAD_V2") ? 2 : 3));
     S->side = (S->fused_head == 3 && !getenv("UKBB_NO_SIDE")) ? 1 : 0;
+    S->first = getenv("UKBB_NO_FIRST") ? 0 : 1;
     {   // class-score layer of head_tc: FP32 weights [k][8] and bias, passed by value (constant bank)
         const ukbb_conv_weights& c = w->conv[UKBB_N_CONV - 1];
         for (int k = 0; k < 64; ++k)
             for (int co = 0; co < 8; ++co) S->h_wl[k * 8 + co] = co < c.cout ? c.kernel[(size_t)k * c.cout + co] : 0.f;
         for (int co = 0; co < 8; ++co) S->h_bias[co] = co < c.cout ? c.bias[co] : -INFINITY;
+    }
+    {   // conv0_0 (CUDA cores): device tap (dy, dx) <- TF kernel[kh = dx][kw = dy], BN scale folded into the FP32 weights
+        const ukbb_conv_weights& c = w->conv[0];
+        for (int co = 0; co < 16; ++co) {
+            const double sc = (double)c.gamma[co] / sqrt((double)c.moving_variance[co] + (double)w->bn_eps);
+            S->c0.shift[co] = (float)((double)c.beta[co] - (double)c.moving_mean[co] * sc);
+            for (int dy = 0; dy < 3; ++dy)
+                for (int dx = 0; dx < 3; ++dx) S->c0.w[dy * 3 + dx][co] = (float)((double)c.kernel[(size_t)(dx * 3 + dy) * 16 + co] * sc);
+        }
     }
     for (int li : {13, 18, 19}) {          // 1x1 layers of the head: fold gamma / sqrt(var + eps) into the weights (head_tc.cuh)
         const ukbb_conv_weights& c = w->conv[li];
@@ -701,7 +736,7 @@ void bf16_release(Engine* h) {
     Bf16State* S = h->tc;
     if (!S) return;
     for (int i = 0; i < UKBB_N_CONV; ++i) { cudaFree(S->w[i]); cudaFree(S->wg[i]); }
-    cudaFree(S->w0); cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
+    cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
     for (int l = 0; l < 5; ++l) { cudaFree(S->t[l]); cudaFree(S->u[l]); }
     cudaFree(S->ones);
     for (int i = 0; i < UKBB_N_CONV; ++i) cudaFree(S->wf[i]);
@@ -901,8 +936,7 @@ static int launch_head_tc2(const Bf16State* S, const HeadParams& hp, int sms, cu
         attr_set = true;
     }
     const int grid = hp.n_tiles < sms ? hp.n_tiles : sms;
-    head_tc_kernel<NC, F16><<<grid, H3_THREADS, H3_SMEM, st>>>(S->hm, hp);
-    UKBB_CUDA(cudaGetLastError());
+    UKBB_CUDA(launch_pdl(head_tc_kernel<NC, F16>, grid, H3_THREADS, H3_SMEM, st, S->hm, hp));
     return UKBB_OK;
 }
 template <bool F16>
@@ -914,8 +948,7 @@ static int launch_side(const Bf16State* S, const SideParams& sp, int sms, cudaSt
     }
     const int n_tiles = sp.tile_start[4];
     const int grid = n_tiles < sms ? n_tiles : sms;
-    side_tc_kernel<F16><<<grid, SD_THREADS, SD_SMEM, st>>>(S->sm, sp);
-    UKBB_CUDA(cudaGetLastError());
+    UKBB_CUDA(launch_pdl(side_tc_kernel<F16>, grid, SD_THREADS, SD_SMEM, st, S->sm, sp));
     return UKBB_OK;
 }
 template <int NC>
@@ -923,6 +956,25 @@ static int launch_head(const Bf16State* S, const HeadParams& hp, int sms, cudaSt
     if (S->fused_head == 3) return S->fp16 ? launch_head_tc2<NC, true>(S, hp, sms, st) : launch_head_tc2<NC, false>(S, hp, sms, st);
     if (S->fused_head == 2) return S->fp16 ? launch_head_mma2<NC, true>(S, hp, sms, st) : launch_head_mma2<NC, false>(S, hp, sms, st);
     return S->fp16 ? launch_head2<NC, true>(S, hp, sms, st) : launch_head2<NC, false>(S, hp, sms, st);
+}
+
+template <bool F16>
+static int launch_first2(const Bf16State* S, const TcLayerPlan& P1, const CUtensorMap& map_img, int nb, int h2, int w2, int sms, cudaStream_t st) {
+    using Cfg = ConvFirstCfg;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(conv_first_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    ConvFirstParams fp;
+    fp.tiles_x = P1.gp.tiles_x; fp.tiles_y = P1.gp.tiles_y; fp.n_tiles = fp.tiles_x * fp.tiles_y * nb;
+    fp.h = h2; fp.w4 = w2 / 4;
+    fp.scale = P1.gp.scale; fp.shift = P1.gp.shift;
+    memcpy(fp.w0, S->c0.w, sizeof(fp.w0));
+    memcpy(fp.shift0, S->c0.shift, sizeof(fp.shift0));
+    const int grid = fp.n_tiles < sms ? fp.n_tiles : sms;
+    UKBB_CUDA(launch_pdl(conv_first_kernel<F16>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, map_img, P1.map_b, P1.map_out, fp));
+    return UKBB_OK;
 }
 
 // Test hook: run ONE tensor-core conv layer of the engine on a caller-provided BF16 NHWC tensor.
@@ -946,21 +998,41 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
     UKBB_REQUIRE((w2 >> 4) >= 1 && (h2 >> 4) >= 1, "forward_bf16: image too small");
     // sub-batch: a multiple of 128 slices would be ideal for the deepest level (bn = 128); keep the
     // activation working set bounded instead
-    int NB = n < 128 ? n : 128;
-    if (S->plan_nb >= n && S->plan_h == h2 && S->plan_w == w2) NB = S->plan_nb;
-    int rc = ensure_plans(h, NB, h2, w2);
+    int cap = 500;
+    if (const char* e = getenv("UKBB_SUBBATCH")) { const int v = atoi(e); if (v > 0) cap = v; }
+    // equal sub-batches (1000 slices -> 2 x 500 rather than 500 + 500 + 0); one SA subject (500 slices) is ONE sub-batch:
+    // measured 151k -> 165k -> 172k slices/s for caps 125 / 250 / 500 (fewer launches, fuller last waves)
+    const int parts = (n + cap - 1) / cap;
+    int NB = (n + parts - 1) / parts;
+    // plans (tensor maps, workspace) built for a larger sub-batch of the same image size serve any smaller one
+    int rc = (S->plan_nb >= NB && S->plan_h == h2 && S->plan_w == w2) ? UKBB_OK : ensure_plans(h, NB, h2, w2);
     if (rc) return rc;
     for (int n0 = 0; n0 < n; n0 += NB) {
         const int nb = n - n0 < NB ? n - n0 : NB;
-        {
+        const bool first = S->first && S->plan[1].kind == 2;
+        if (first) {
+            // conv0_0 + conv0_1 in one launch; the image box map names this call's image pointer
+            CUtensorMap map_img;
+            cuuint64_t dims[3] = {(cuuint64_t)w2, (cuuint64_t)h2, (cuuint64_t)nb};
+            cuuint64_t strides[2] = {(cuuint64_t)w2 * 4, (cuuint64_t)h2 * w2 * 4};
+            cuuint32_t box[3] = {ConvFirstCfg::IMG_W, ConvFirstCfg::IMG_H, 1}, e3[3] = {1, 1, 1};
+            CUresult r = S->encode(&map_img, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(image + (size_t)n0 * h2 * w2), dims, strides, box, e3,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(image boxes) failed: %d", (int)r); return UKBB_E_CUDA; }
+            rc = S->fp16 ? launch_first2<true>(S, S->plan[1], map_img, nb, h2, w2, h->sms, st)
+                         : launch_first2<false>(S, S->plan[1], map_img, nb, h2, w2, h->sms, st);
+            if (rc) return rc;
+            h->launches++;
+        } else {
             const long long total = (long long)nb * h2 * w2;
-            conv0_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-                image + (size_t)n0 * h2 * w2, h->layers[0].w_f32, h->layers[0].scale, h->layers[0].shift,
-                (__nv_bfloat16*)h->ws.a[0], total, h2, w2, S->fp16);
+            const unsigned grid0 = (unsigned)((total + 255) / 256);
+            if (S->fp16) conv0_bf16_kernel<true><<<grid0, 256, 0, st>>>(image + (size_t)n0 * h2 * w2, (__nv_bfloat16*)h->ws.a[0], total, h2, w2, S->c0);
+            else conv0_bf16_kernel<false><<<grid0, 256, 0, st>>>(image + (size_t)n0 * h2 * w2, (__nv_bfloat16*)h->ws.a[0], total, h2, w2, S->c0);
             UKBB_CUDA(cudaGetLastError());
             h->launches++;
         }
-        for (int li = 1; li < 18; ++li) {
+        for (int li = first ? 2 : 1; li < 18; ++li) {
             if (li == 13 && S->fused_head >= 2) continue;        // same_dim0 lives inside head_mma_kernel
             if (li > 13 && S->side) break;                       // same_dim 1..4 live inside side_tc_kernel
             TcLayerPlan P = S->plan[li];

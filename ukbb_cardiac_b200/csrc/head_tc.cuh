@@ -58,6 +58,7 @@ template <int NC, bool F16>
 __global__ void __launch_bounds__(H3_THREADS, 1)
 head_tc_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__ HeadParams p) {
     using namespace tc;
+    griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -111,6 +112,7 @@ head_tc_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp != 12) griddep_wait();                      // the producer waits after it has issued the weight loads
     // pre-arrivals standing for the "accumulator drained" signals that the first tiles have no predecessor for
     if (warp < 4 && lane == 0) {
         for (int s3 = 0; s3 < H3_STAGES; ++s3) mbar_arrive(BAR(IN_FULL + s3));
@@ -139,6 +141,7 @@ head_tc_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             tma_load_2d(w0_base, &maps.w0, BAR(WFULL), 0, 0);
             tma_load_2d(w1_base, &maps.w1, BAR(WFULL), 0, 0);
         }
+        griddep_wait();
         __syncwarp();
         TileWalk w;
         w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);

@@ -60,6 +60,7 @@ template <bool F16>
 __global__ void __launch_bounds__(SD_THREADS, 1)
 side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ SideParams p) {
     using namespace tc;
+    griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -104,6 +105,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp != 0) griddep_wait();                       // the producer waits after it has issued the weight loads
     const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     auto LO = [](uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); };
     constexpr uint32_t HI64 = (uint32_t)((8 * 64) >> 4) | (1u << 14) | (4u << 29);
@@ -119,6 +121,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
             for (int l = 2; l <= 4; ++l)
                 for (int c = 0; c < (1 << (l - 2)); ++c) tma_load_2d(wsd_base + sd_wsd_off(l) + c * 4096, &maps.wsd[l - 1], BAR(WFULL), c * 64, 0);
             for (int l = 1; l <= 4; ++l) tma_load_2d(wl_base + (l - 1) * 4096, &maps.w0, BAR(WFULL), 32 * l, 0);
+            griddep_wait();
             int slot = 0;
             uint32_t ph = 0;
             for (int i = 0; i < my_tiles; ++i) {

@@ -52,9 +52,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(20000u)     // suspend-time hint (ns): sleep in hardware instead of re-issuing the probe
             : "memory");
-        if (!done && spins > (1u << 22)) __trap();
+        if (!done && spins > (1u << 22)) {
+#ifdef UKBB_DEBUG_MBAR
+            printf("mbar timeout: bar %x parity %u block %d thread %d\n", bar, parity, (int)blockIdx.x, (int)threadIdx.x);
+#endif
+            __trap();
+        }
     }
 }
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every tensor-core kernel of the forward is launched with programmatic stream serialization: its CTAs may start
+// (barrier init, TMEM allocation, weight loads) while the previous kernel drains its last tiles.  griddep_wait()
+// blocks until the previous kernel has completed and its writes are visible; it must precede the first access to
+// activation memory.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
