@@ -204,3 +204,23 @@ def test_first_kernel_bit_identical(monkeypatch, mode, shape):
     assert n_plain - n_first == SUB_BATCHES(shape[0])                   # 2 launches became 1 per sub-batch
     assert torch.equal(g1, g2)
     assert torch.equal(l1, l2)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("n_class,shape", [(4, (3, 64, 96)), (2, (5, 48, 80)), (3, (2, 208, 192)), (6, (9, 32, 48))])
+def test_head_ts_bit_identical(monkeypatch, mode, n_class, shape):
+    """head_ts_kernel keeps U_l / A0 / A2 in tensor memory (tcgen05.st + tcgen05.mma with a [tmem] A operand);
+    it issues the same UMMAs in the same order on the same 16-bit values as head_tc_kernel, whose A operands
+    live in shared memory: logits and labels are bit-identical."""
+    w = synth.make_weights(0, n_class)
+    img = np.random.default_rng(shape[2]).random(shape + (1,)).astype(np.float32)
+    dev = to_device_layout(img)
+    with FCNEngine(w, mode=mode) as eng:
+        l1, g1, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+    monkeypatch.setenv("UKBB_HEAD_V3", "1")
+    with FCNEngine(w, mode=mode) as eng:
+        l2, g2, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+    assert torch.equal(g1, g2)
+    assert torch.equal(l1, l2)

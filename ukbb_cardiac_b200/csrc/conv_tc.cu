@@ -22,6 +22,7 @@
 #include "head_fused.cuh"
 #include "head_mma.cuh"
 #include "head_tc.cuh"
+#include "head_ts.cuh"
 #include "side_tc.cuh"
 #include <stdlib.h>
 #include <math.h>
@@ -399,8 +400,9 @@ struct Bf16State {
     TcLayerPlan plan[UKBB_N_CONV];
     int plan_nb = 0, plan_h = 0, plan_w = 0;
     int fp16 = 0;
-    int fused_head = 3;                      // 0 = unfused, 1 = gather head (head_fused), 2 = tensor-core upsample (head_mma),
-                                             // 3 = head_mma algebra + tensor-core class scores, 4-stage pipeline (head_tc)
+    int fused_head = 4;                      // 0 = unfused, 1 = gather head (head_fused), 2 = tensor-core upsample (head_mma),
+                                             // 3 = head_mma algebra, 4-stage pipeline, constant-bank epilogues (head_tc),
+                                             // 4 = head_tc with the A operands (U_l, A0, A2) in tensor memory (head_ts)
     __nv_bfloat16* wf[UKBB_N_CONV] = {};     // head_tc: weights of same_dim0 / fc0 / fc1 with the BN scale folded in before rounding
     float h_shift[UKBB_N_CONV][64] = {};     // host copies of the folded-BN shifts of those layers (constant-bank operands)
     float h_bias[8] = {};
@@ -626,8 +628,8 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
     if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return UKBB_E_CUDA; }
     S->encode = (EncodeTiledFn)fn;
     S->fp16 = h->mode == UKBB_MODE_FP16 ? 1 : 0;
-    S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : (getenv("UKBB_HEAD_GATHER") ? 1 : (getenv("UKBB_HEAD_V2") ? 2 : 3));
-    S->side = (S->fused_head == 3 && !getenv("UKBB_NO_SIDE")) ? 1 : 0;
+    S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : (getenv("UKBB_HEAD_GATHER") ? 1 : (getenv("UKBB_HEAD_V2") ? 2 : (getenv("UKBB_HEAD_V3") ? 3 : 4)));
+    S->side = (S->fused_head >= 3 && !getenv("UKBB_NO_SIDE")) ? 1 : 0;
     S->first = getenv("UKBB_NO_FIRST") ? 0 : 1;
     {   // class-score layer of head_tc: FP32 weights [k][8] and bias, passed by value (constant bank)
         const ukbb_conv_weights& c = w->conv[UKBB_N_CONV - 1];
@@ -819,7 +821,7 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
             S->tplan[l].p.kofs = 32 * l;
             {   // weight map must span all 160 K columns: rebuild it (make_plan used cin = 32)
                 cuuint64_t d0[2] = {160, 64}; cuuint64_t st0[1] = {320}; cuuint32_t b0[2] = {32, 64};
-                CUresult r = S->encode(&S->tplan[l].map_b, dt16, 2, S->fused_head == 3 ? S->wf[18] : S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CUresult r = S->encode(&S->tplan[l].map_b, dt16, 2, S->fused_head >= 3 ? S->wf[18] : S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(t-layer weights) failed: %d", (int)r); return UKBB_E_CUDA; }
             }
@@ -878,11 +880,11 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         cuuint64_t d0[2] = {160, 64}; cuuint64_t st0[1] = {320}; cuuint32_t b0[2] = {32, 64}; cuuint32_t e2[2] = {1, 1};
         if (r == CUDA_SUCCESS)
-            r = S->encode(&S->map_w0, dt16, 2, S->fused_head == 3 ? S->wf[18] : S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            r = S->encode(&S->map_w0, dt16, 2, S->fused_head >= 3 ? S->wf[18] : S->w[18], d0, st0, b0, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         cuuint64_t d1[2] = {64, 64}; cuuint64_t st1[1] = {128}; cuuint32_t b1[2] = {64, 64};
         if (r == CUDA_SUCCESS)
-            r = S->encode(&S->map_w1, dt16, 2, S->fused_head == 3 ? S->wf[19] : S->w[19], d1, st1, b1, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            r = S->encode(&S->map_w1, dt16, 2, S->fused_head >= 3 ? S->wf[19] : S->w[19], d1, st1, b1, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(fused head) failed: %d", (int)r); return UKBB_E_CUDA; }
         S->hm.s0 = S->map_s0; S->hm.w0 = S->map_w0; S->hm.w1 = S->map_w1;
@@ -895,7 +897,7 @@ static int ensure_plans(Engine* h, int nb, int h2, int w2) {
                           CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             cuuint64_t dsd[2] = {16, 32}; cuuint64_t ssd[1] = {32}; cuuint32_t bsd[2] = {16, 32};
             if (r == CUDA_SUCCESS)
-                r = S->encode(&S->hm.wsd, dt16, 2, S->fused_head == 3 ? S->wf[13] : S->w[13], dsd, ssd, bsd, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                r = S->encode(&S->hm.wsd, dt16, 2, S->fused_head >= 3 ? S->wf[13] : S->w[13], dsd, ssd, bsd, e2, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(head same_dim0) failed: %d", (int)r); return UKBB_E_CUDA; }
         }
@@ -939,6 +941,17 @@ static int launch_head_tc2(const Bf16State* S, const HeadParams& hp, int sms, cu
     UKBB_CUDA(launch_pdl(head_tc_kernel<NC, F16>, grid, H3_THREADS, H3_SMEM, st, S->hm, hp));
     return UKBB_OK;
 }
+template <int NC, bool F16>
+static int launch_head_ts2(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        UKBB_CUDA(cudaFuncSetAttribute(head_ts_kernel<NC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H4_SMEM));
+        attr_set = true;
+    }
+    const int grid = hp.n_tiles < sms ? hp.n_tiles : sms;
+    UKBB_CUDA(launch_pdl(head_ts_kernel<NC, F16>, grid, H4_THREADS, H4_SMEM, st, S->hm, hp));
+    return UKBB_OK;
+}
 template <bool F16>
 static int launch_side(const Bf16State* S, const SideParams& sp, int sms, cudaStream_t st) {
     static bool attr_set = false;
@@ -953,6 +966,7 @@ static int launch_side(const Bf16State* S, const SideParams& sp, int sms, cudaSt
 }
 template <int NC>
 static int launch_head(const Bf16State* S, const HeadParams& hp, int sms, cudaStream_t st) {
+    if (S->fused_head == 4) return S->fp16 ? launch_head_ts2<NC, true>(S, hp, sms, st) : launch_head_ts2<NC, false>(S, hp, sms, st);
     if (S->fused_head == 3) return S->fp16 ? launch_head_tc2<NC, true>(S, hp, sms, st) : launch_head_tc2<NC, false>(S, hp, sms, st);
     if (S->fused_head == 2) return S->fp16 ? launch_head_mma2<NC, true>(S, hp, sms, st) : launch_head_mma2<NC, false>(S, hp, sms, st);
     return S->fp16 ? launch_head2<NC, true>(S, hp, sms, st) : launch_head2<NC, false>(S, hp, sms, st);
@@ -1083,6 +1097,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             memcpy(hp.c_shift0, S->h_shift[18], sizeof(hp.c_shift0));
             memcpy(hp.c_shift1, S->h_shift[19], sizeof(hp.c_shift1));
             memcpy(hp.c_bias, S->h_bias, sizeof(hp.c_bias));
+            for (int l = 0; l < 5; ++l) hp.u_glob[l] = (const uint32_t*)S->u[l];
             for (int k2 = 0; k2 < 32; ++k2)
                 for (int c = 0; c < 8; ++c) hp.c_wl2[k2][c] = make_float2(S->h_wl[(2 * k2) * 8 + c], S->h_wl[(2 * k2 + 1) * 8 + c]);
             const size_t po = (size_t)n0 * h2 * w2 * h->n_class;

@@ -42,6 +42,7 @@ struct HeadParams {
     // epilogues read them as constant-bank operands (no shared-memory loads, no registers)
     float c_shift_sd0[32], c_shift0[64], c_shift1[64], c_bias[8];
     float2 c_wl2[32][8];            // class-score weights FP32 as input-channel pairs: [k / 2][class] = (w[k][c], w[k + 1][c])
+    const uint32_t* u_glob[5];      // head_ts only: interpolation matrices U_l in global memory, rows of HM_KPAD[l] 16-bit values
 };
 
 constexpr int HEAD_THREADS = 448;
