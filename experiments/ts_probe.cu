@@ -113,6 +113,38 @@ probe(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
         ph ^= 1;
         tc_fence_before(); __syncthreads(); tc_fence_after();
     }
+    // ---- 3. latency: n MMAs + commit -> barrier completion seen by the issuing warp (cycles)
+    for (int mode = 0; mode < 2; ++mode)
+        for (int n = 1; n <= 9; n += 4) {
+            if (warp == 0) {
+                const bool leader = elect_one();
+                const uint32_t a_lo = ((asm_ & 0x3FFFF) >> 4) | (1u << 16), b_lo = ((bsm & 0x3FFFF) >> 4) | (1u << 16);
+                constexpr uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+                long long best = 1ll << 60;
+                for (int rep = 0; rep < 8; ++rep) {
+                    const long long t0 = clock64();
+                    if (leader) {
+                        for (int k = 0; k < n; ++k) {
+                            if (mode == 0)
+                                asm volatile("{\n.reg .pred p;\n.reg .b64 db;\nsetp.ne.b32 p, %5, 0;\nmov.b64 db, {%2, %3};\n"
+                                             "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n}\n" ::"r"(tmem), "r"(tmem + A_COL + 8 * (k & 3)),
+                                             "r"(b_lo + 2 * (k & 3)), "r"(hi), "r"(idesc), "r"(1u)
+                                             : "memory");
+                            else umma_bf16_lohi(tmem, a_lo + 2 * (k & 3), hi, b_lo + 2 * (k & 3), hi, idesc, 1u);
+                        }
+                        umma_commit(bar2);
+                    }
+                    __syncwarp();
+                    mbar_wait(bar2, ph); ph ^= 1;
+                    const long long dt = clock64() - t0;
+                    if (dt < best) best = dt;
+                }
+                if (lane == 0) cyc[2 + mode * 3 + n / 4] = best;
+            } else {
+                for (int rep = 0; rep < 8; ++rep) ph ^= 1;
+            }
+            tc_fence_before(); __syncthreads(); tc_fence_after();
+        }
     tc_fence_before(); __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
@@ -132,13 +164,13 @@ int main() {
       if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, da, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) { printf("encode a failed\n"); return 1; } }
     { cuuint64_t d[2] = {64, 64}; cuuint64_t s[1] = {128}; cuuint32_t b[2] = {64, 64}; cuuint32_t e[2] = {1, 1};
       if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, db, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) { printf("encode b failed\n"); return 1; } }
-    float* dout; long long* dc; CK(cudaMalloc(&dout, 128 * 128 * 4)); CK(cudaMalloc(&dc, 16));
+    float* dout; long long* dc; CK(cudaMalloc(&dout, 128 * 128 * 4)); CK(cudaMalloc(&dc, 64));
     const int smem = 16384 + 8192 + 1024 + 64, iters = 256;
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     probe<<<1, 128, smem>>>(ma, mb, da, dout, dc, iters);
     CK(cudaDeviceSynchronize());
-    std::vector<float> ho(128 * 128); long long hc[2];
-    CK(cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+    std::vector<float> ho(128 * 128); long long hc[8];
+    CK(cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hc, dc, 64, cudaMemcpyDeviceToHost));
     int bad_ts = 0, bad_ss = 0;
     for (int m = 0; m < 128; ++m) for (int k = 0; k < 64; ++k) {
         const float want = (float)((m * 3 + k * 5) % 251);
@@ -148,5 +180,6 @@ int main() {
     printf("A from TMEM: %d mismatches; A from shared memory: %d mismatches\n", bad_ts, bad_ss);
     if (bad_ts) { printf("row 1, TS:"); for (int k = 0; k < 16; ++k) printf(" %g", ho[128 + k]); printf("\nwant      :"); for (int k = 0; k < 16; ++k) printf(" %d", (3 + k * 5) % 251); printf("\n"); }
     printf("cycles per MMA (M=128, N=64, K=16): A from TMEM %.1f, A from shared memory %.1f\n", (double)hc[0] / (iters * 16), (double)hc[1] / (iters * 16));
+    printf("latency issue -> commit seen (cycles): A from TMEM n=1 %lld, n=5 %lld, n=9 %lld; A from smem n=1 %lld, n=5 %lld, n=9 %lld\n", hc[2], hc[3], hc[4], hc[5], hc[6], hc[7]);
     return 0;
 }

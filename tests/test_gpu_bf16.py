@@ -208,10 +208,11 @@ def test_first_kernel_bit_identical(monkeypatch, mode, shape):
 
 @pytest.mark.parametrize("mode", ["bf16", "fp16"])
 @pytest.mark.parametrize("n_class,shape", [(4, (3, 64, 96)), (2, (5, 48, 80)), (3, (2, 208, 192)), (6, (9, 32, 48))])
-def test_head_ts_bit_identical(monkeypatch, mode, n_class, shape):
-    """head_ts_kernel keeps U_l / A0 / A2 in tensor memory (tcgen05.st + tcgen05.mma with a [tmem] A operand);
-    it issues the same UMMAs in the same order on the same 16-bit values as head_tc_kernel, whose A operands
-    live in shared memory: logits and labels are bit-identical."""
+def test_head_ts_matches_head_tc(monkeypatch, mode, n_class, shape):
+    """head_ts_kernel keeps U_l / b0 / A0 / A2 in tensor memory (tcgen05.st + tcgen05.mma with a [tmem] A operand) and
+    issues the same UMMAs in the same order on the same 16-bit values as head_tc_kernel, whose A operands live in
+    shared memory; only the FP32 class-score epilogue is re-associated (relu(d + s) . w = max(d, -s) . w + s . w with the
+    constant folded into the bias).  Logits agree to FP32 rounding, labels everywhere but at exact near-ties."""
     w = synth.make_weights(0, n_class)
     img = np.random.default_rng(shape[2]).random(shape + (1,)).astype(np.float32)
     dev = to_device_layout(img)
@@ -222,5 +223,6 @@ def test_head_ts_bit_identical(monkeypatch, mode, n_class, shape):
     with FCNEngine(w, mode=mode) as eng:
         l2, g2, _ = eng.forward(dev, want_logits=True)
         torch.cuda.synchronize()
-    assert torch.equal(g1, g2)
-    assert torch.equal(l1, l2)
+    rel = float((g1 - g2).abs().max() / g2.abs().max())
+    assert rel < 2e-6, rel
+    assert float((l1 != l2).float().mean()) < 1e-4

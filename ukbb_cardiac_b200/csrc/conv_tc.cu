@@ -1098,6 +1098,24 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             memcpy(hp.c_shift1, S->h_shift[19], sizeof(hp.c_shift1));
             memcpy(hp.c_bias, S->h_bias, sizeof(hp.c_bias));
             for (int l = 0; l < 5; ++l) hp.u_glob[l] = (const uint32_t*)S->u[l];
+            hp.b0 = (const uint4*)h->ws.b[0];
+            hp.dbg = getenv("UKBB_HEAD_DBG") ? atoi(getenv("UKBB_HEAD_DBG")) : 0;
+            hp.trace = nullptr;
+            static long long* d_trace = nullptr;
+            if (hp.dbg & 16) {
+                if (!d_trace) { UKBB_CUDA(cudaMalloc(&d_trace, 12 * 64 * sizeof(long long))); }
+                UKBB_CUDA(cudaMemsetAsync(d_trace, 0, 12 * 64 * sizeof(long long), st));
+                hp.trace = d_trace;
+            }
+            for (int k = 0; k < 64; ++k) {
+                hp.c_nshift1[k] = -S->h_shift[19][k];
+                for (int c = 0; c < 8; ++c) hp.c_wlc[k][c] = S->h_wl[k * 8 + c];
+            }
+            for (int c = 0; c < 8; ++c) {
+                double acc = 0.0;
+                for (int k = 0; k < 64; ++k) acc += (double)S->h_shift[19][k] * (double)S->h_wl[k * 8 + c];
+                hp.c_bias2[c] = c < h->n_class ? (float)((double)S->h_bias[c] + acc) : -INFINITY;
+            }
             for (int k2 = 0; k2 < 32; ++k2)
                 for (int c = 0; c < 8; ++c) hp.c_wl2[k2][c] = make_float2(S->h_wl[(2 * k2) * 8 + c], S->h_wl[(2 * k2 + 1) * 8 + c]);
             const size_t po = (size_t)n0 * h2 * w2 * h->n_class;
@@ -1114,6 +1132,12 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             }
             if (rc) return rc;
             h->launches++;
+            if ((hp.dbg & 16) && getenv("UKBB_HEAD_TRACE")) {       // experiment: dump the timeline of CTA 0
+                long long ht[12 * 64];
+                UKBB_CUDA(cudaStreamSynchronize(st));
+                UKBB_CUDA(cudaMemcpy(ht, hp.trace, sizeof(ht), cudaMemcpyDeviceToHost));
+                if (FILE* f = fopen(getenv("UKBB_HEAD_TRACE"), "wb")) { fwrite(ht, 1, sizeof(ht), f); fclose(f); }
+            }
             continue;
         }
         {

@@ -43,6 +43,12 @@ struct HeadParams {
     float c_shift_sd0[32], c_shift0[64], c_shift1[64], c_bias[8];
     float2 c_wl2[32][8];            // class-score weights FP32 as input-channel pairs: [k / 2][class] = (w[k][c], w[k + 1][c])
     const uint32_t* u_glob[5];      // head_ts only: interpolation matrices U_l in global memory, rows of HM_KPAD[l] 16-bit values
+    const uint4* b0;                // head_ts only: conv0_1 output [n][h][w][16] 16-bit (level-0 input of same_dim0)
+    float c_nshift1[64];            // head_ts only: -shift of fc1;  relu(d + s) . w = max(d, -s) . w + s . w
+    float c_bias2[8];               //   bias + sum_k shift1[k] * w[k][c]  (-inf for c >= n_class)
+    float c_wlc[64][8];             //   class-score weights [k][class], zero for c >= n_class
+    int dbg;                        // experiments (UKBB_HEAD_DBG): 1 short E2, 2 no patch loads, 4 no U terms, 8 no b0 loads, 16 timeline trace
+    long long* trace;               // [12 events][64 tiles] clock64 of CTA 0 (dbg & 16)
 };
 
 constexpr int HEAD_THREADS = 448;

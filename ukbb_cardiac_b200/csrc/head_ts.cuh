@@ -14,14 +14,17 @@
 //     stores, no proxy fence,
 //   * S1 / S2 issue tcgen05.mma with [tmem] A operands; only the B operands (weights, TMA-written t_l
 //     patches) and the b0 tile of S0 are read from shared memory: ~40 KB per tile instead of ~120 KB.
-// TMEM columns (512): D0 3 x 32 | D1 2 x 64 | D2 2 x 64 | A0 2 x 16 | A2 2 x 32 | U 64.
+//   * the level-0 input b0 (16 channels) never touches shared memory either: the E0 warps read their pixel's 32 bytes
+//     with two LDG.128 two tiles ahead and tcgen05.st them as the A operand of S0 (the 128-row TMA box it replaces was the
+//     most expensive of the five loads per tile: TMA moves about one box row per cycle, profiles/r1_tma_probe3.log),
+// TMEM columns (512): D0 2 x 32 | B0 3 x 8 | D1 2 x 64 | D2 2 x 64 | A0 2 x 16 | A2 2 x 32 | U 64.
 //
-//   S0  D0[128x32] = b0_tile[128x16] . Wsd0^T                      (1 UMMA,  N = 32, A from smem)   MMA warp 13
-//   E0  A0 = relu(D0 + shift_sd0) -> 16 bit -> TMEM                                                  warps 0-3
-//   S1  D1[128x64] = A0 . W_0^T + sum_l U_l . t_l patch             (2 + 7 UMMAs, A from TMEM)       MMA warp 14
-//   E1  A2 = relu(D1 + shift_fc0) -> 16 bit -> TMEM                                                  warps 0-3
-//   S2  D2[128x64] = A2 . W_fc1^T                                   (4 UMMAs, A from TMEM)           MMA warp 15
-//   E2  f = relu(D2 + shift_fc1) in FP32, class scores in FP32, softmax / argmax / crop / counts      warps 4-11
+//   S0  D0[128x32] = b0_tile[128x16] . Wsd0^T                      (1 UMMA,  N = 32, A from TMEM)   MMA warp 17
+//   E0  A0 = relu(D0 + shift_sd0) -> 16 bit -> TMEM; b0 of tile i + 2 -> TMEM                          warps 0-3
+//   S1  D1[128x64] = A0 . W_0^T + sum_l U_l . t_l patch             (2 + 7 UMMAs, A from TMEM)       MMA warp 18
+//   E1  A2 = relu(D1 + shift_fc0) -> 16 bit -> TMEM                                                  warps 4-7
+//   S2  D2[128x64] = A2 . W_fc1^T                                   (4 UMMAs, A from TMEM)           MMA warp 19
+//   E2  f = relu(D2 + shift_fc1) in FP32, class scores in FP32, softmax / argmax / crop / counts      warps 8-15
 //       (train_network.py:198-199, deploy_network.py:114-130) -- unchanged from head_tc.cuh
 #pragma once
 #include "tc_common.cuh"
@@ -69,12 +72,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 }  // namespace tc
 
-constexpr int H4_THREADS = 512;
-constexpr int H4_STAGES = 6;                                      // input stages
-constexpr int H4_D0S = 3;                                         // same_dim0 accumulator stages
+constexpr int H4_E2SETS = 3;                                      // E2 warp sets (4 warps each), tile i -> set i % 3
+constexpr int H4_THREADS = 928;                                   // 29 warps: 0-3 E0, 4-7 E1, 8-19 E2 (3 sets), 20 TMA, 21 S0, 22 / 23 S1 even / odd tiles, 24 S2, 25-28 b0 loaders
+constexpr int H4_STAGES = 10;                                     // input stages (t_l patches): ~2000 cycles of TMA latency at ~700 cycles per tile
+constexpr int H4_D0S = 2;                                         // same_dim0 accumulator stages
+constexpr int H4_B0S = 3;                                         // b0 operand stages in TMEM (8 columns each)
 constexpr int H4_SMEM = H4_STAGES * HM_IN_BYTES + HM_W0 + HM_W1 + HM_WSD + 1024 /*align*/ + 512 /*barriers*/;
 // TMEM columns
-constexpr int H4_D0 = 0, H4_D1 = 96, H4_D2 = 224, H4_A0 = 352, H4_A2 = 384, H4_U1 = 448, H4_U2 = 472, H4_U3 = 488, H4_U4 = 496;
+constexpr int H4_D0 = 0, H4_B0 = 64, H4_D1 = 96, H4_D2 = 224, H4_A0 = 352, H4_A2 = 384, H4_U1 = 448, H4_U2 = 472, H4_U3 = 488, H4_U4 = 496;
 
 template <int NC, bool F16>
 __global__ void __launch_bounds__(H4_THREADS, 1)
@@ -91,29 +96,33 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
     const uint32_t bar_base = wsd_base + HM_WSD;
     auto BAR = [&](int i) { return bar_base + 8u * i; };
     enum { WFULL = 0, UFULL = 1, IN_FULL = 2, IN_EMPTY = IN_FULL + H4_STAGES, D0_FULL = IN_EMPTY + H4_STAGES, D0_EMPTY = D0_FULL + H4_D0S,
-           A0_FULL = D0_EMPTY + H4_D0S, A0_EMPTY = A0_FULL + 2, D1_FULL = A0_EMPTY + 2, D1_EMPTY = D1_FULL + 2, A2_FULL = D1_EMPTY + 2,
-           A2_EMPTY = A2_FULL + 2, D2_FULL = A2_EMPTY + 2, D2_EMPTY = D2_FULL + 2, TSLOT = D2_EMPTY + 2 };
+           B0_FULL = D0_EMPTY + H4_D0S, B0_EMPTY = B0_FULL + H4_B0S, A0_FULL = B0_EMPTY + H4_B0S, A0_EMPTY = A0_FULL + 2, D1_FULL = A0_EMPTY + 2, D1_EMPTY = D1_FULL + 2, A2_FULL = D1_EMPTY + 2,
+           A2_EMPTY = A2_FULL + 2, D2_FULL = A2_EMPTY + 2, D2_EMPTY = D2_FULL + 6, TSLOT = D2_EMPTY + 6 };
+    // D2 has two TMEM buffers (tile i -> i & 1) but SIX barrier pairs (tile i -> i % 6): with three E2 warp sets (tile i -> set i % 3) a
+    // barrier must belong to one set only -- a parity wait can tell the current phase from the previous one, not from the one before
     static_assert((TSLOT + 1) * 8 <= 512, "barrier area");
     const uint32_t tmem_slot = BAR(TSLOT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp == 12 && lane == 0) {
+    if (warp == 20 && lane == 0) {
         const CUtensorMap* m = &maps.s0;
         for (int i = 0; i < 12; ++i) tma_prefetch_desc(m + i);
     }
-    if (warp == 13 && lane == 0) {
+    if (warp == 21 && lane == 0) {
         mbar_init(BAR(WFULL), 1);
         mbar_init(BAR(UFULL), 4);
         for (int s = 0; s < H4_STAGES; ++s) { mbar_init(BAR(IN_FULL + s), 1); mbar_init(BAR(IN_EMPTY + s), 1); }
         for (int d = 0; d < H4_D0S; ++d) { mbar_init(BAR(D0_FULL + d), 1); mbar_init(BAR(D0_EMPTY + d), 4); }
+        for (int d = 0; d < H4_B0S; ++d) { mbar_init(BAR(B0_FULL + d), 4); mbar_init(BAR(B0_EMPTY + d), 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(BAR(A0_FULL + b), 4); mbar_init(BAR(A0_EMPTY + b), 1); mbar_init(BAR(D1_FULL + b), 1); mbar_init(BAR(D1_EMPTY + b), 4);
-            mbar_init(BAR(A2_FULL + b), 4); mbar_init(BAR(A2_EMPTY + b), 1); mbar_init(BAR(D2_FULL + b), 1); mbar_init(BAR(D2_EMPTY + b), 4);
+            mbar_init(BAR(A2_FULL + b), 4); mbar_init(BAR(A2_EMPTY + b), 1);
         }
+        for (int k = 0; k < 6; ++k) { mbar_init(BAR(D2_FULL + k), 1); mbar_init(BAR(D2_EMPTY + k), 4); }
         fence_barrier_init();
     }
-    if (warp == 15) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (warp == 24) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     // zero the input stages once: the K-padding rows of the t_l patches are never written by TMA and
     // must be finite (they meet zero columns of U_l)
     for (int i = threadIdx.x; i < H4_STAGES * HM_IN_BYTES / 16; i += H4_THREADS)
@@ -124,15 +133,17 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    if (warp != 12) griddep_wait();                      // the producer waits after it has issued the weight loads
+    if (warp != 20) griddep_wait();                      // the producer waits after it has issued the weight loads
     const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     auto LO = [](uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); };
+    const bool tracing = (p.dbg & 16) && blockIdx.x == 0 && p.trace != nullptr;
+    auto TRACE = [&](int ev, int tile) { if (tracing && lane == 0 && tile < 64) p.trace[ev * 64 + tile] = clock64(); };
     constexpr uint32_t HI32 = (uint32_t)((8 * 32) >> 4) | (1u << 14) | (6u << 29);
     constexpr uint32_t HI64 = (uint32_t)((8 * 64) >> 4) | (1u << 14) | (4u << 29);
     constexpr uint32_t HI128 = (uint32_t)((8 * 128) >> 4) | (1u << 14) | (2u << 29);
 
-    if (warp == 12) {
-        // ===================== TMA producer (as head_tc: five box loads per tile in one warp instruction) =====================
+    if (warp == 20) {
+        // ===================== TMA producer: the four t_l patch loads of a tile are one warp instruction (lanes 1-4) =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(BAR(WFULL), HM_W0 + HM_W1 + HM_WSD);
             tma_load_2d(wsd_base, &maps.wsd, BAR(WFULL), 0, 0);
@@ -153,17 +164,18 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
         for (int i = 0; i < my_tiles; ++i) {
             const int y0 = w.ty * 8, x0 = w.tx * 16, n = w.n;
             mbar_wait(BAR(IN_EMPTY + s), ph ^ 1);
+            TRACE(0, i);
             const uint32_t dst = in_base + s * HM_IN_BYTES;
             const uint32_t fullb = BAR(IN_FULL + s);
-            if (lane == 0) mbar_arrive_expect_tx(fullb, HM_IN_TX);
+            if (lane == 0) { if (p.dbg & 2) mbar_arrive(fullb); else mbar_arrive_expect_tx(fullb, HM_IN_TX - HM_IN_S0); }   // t_l patches only: b0 goes through registers
             __syncwarp();
-            if (lane < 5) tma_load_4d(dst + my_off, my_map, fullb, 0, ((x0 + pb) >> l) - back, ((y0 + pb) >> l) - back, n);
+            if (lane >= 1 && lane < 5 && !(p.dbg & 2)) tma_load_4d(dst + my_off, my_map, fullb, 0, ((x0 + pb) >> l) - back, ((y0 + pb) >> l) - back, n);
             __syncwarp();
             if (++s == H4_STAGES) { s = 0; ph ^= 1; }
             w.next();
         }
-    } else if (warp == 13) {
-        // ===================== MMA issuer 0: same_dim0 (S0), A = b0 tile in shared memory =====================
+    } else if (warp == 21) {
+        // ===================== MMA issuer 0: same_dim0 (S0), A = b0 tile in TMEM (written by the E0 warps) =====================
         const bool leader = elect_one();
         const uint32_t idesc_sd = F16 ? make_idesc_f16(128, 32) : make_idesc_bf16(128, 32);
         const uint32_t wsd_lo = LO(wsd_base);
@@ -173,18 +185,23 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
         uint32_t ph = 0, dph = 0;
         for (int i = 0; i < my_tiles; ++i) {
             mbar_wait(BAR(D0_EMPTY + d), dph ^ 1);
-            mbar_wait(BAR(IN_FULL + s), ph);
+            mbar_wait(BAR(B0_FULL + s), ph);
             tc_fence_after();
+            TRACE(1, i);
             if (leader) {
-                umma_bf16_lohi(tmem_base + H4_D0 + d * 32, LO(in_base + s * HM_IN_BYTES), HI32, wsd_lo, HI32, idesc_sd, 0u);
+                umma_ts_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 8, wsd_lo, HI32, idesc_sd, 0u);
+                umma_commit(BAR(B0_EMPTY + s));
                 umma_commit(BAR(D0_FULL + d));
             }
             __syncwarp();
-            if (++s == H4_STAGES) { s = 0; ph ^= 1; }
+            if (++s == H4_B0S) { s = 0; ph ^= 1; }
             if (++d == H4_D0S) { d = 0; dph ^= 1; }
         }
-    } else if (warp == 14) {
-        // ===================== MMA issuer 1: fc0 with the upsample terms (S1), A operands in TMEM =====================
+    } else if (warp == 22 || warp == 23) {
+        // ===================== MMA issuers 1a / 1b: fc0 with the upsample terms (S1), A operands in TMEM =====================
+        // Two warps, even / odd tiles: one issuer needed ~1000 cycles per tile (150 dependent scalar instructions of loop, barrier and
+        // descriptor bookkeeping at ~4.4 cycles each + 12 queue-limited tcgen05 issues) and was what every other role waited for.
+        const int par = warp - 22;
         const bool leader = elect_one();
         const uint32_t idesc_kk = F16 ? make_idesc_f16(128, 64) : make_idesc_bf16(128, 64);
         const uint32_t idesc_kmn = idesc_kk | (1u << 16);            // B operand MN-major (pixel-major t_l patch)
@@ -193,21 +210,25 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
         mbar_wait(BAR(UFULL), 0);
         tc_fence_after();
         TileWalk w;                                                 // needs the tile-row parity for U_4
-        w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
-        int s = 0;
-        for (int i = 0; i < my_tiles; ++i) {
-            const int b = i & 1;
+        w.init(blockIdx.x + par * gridDim.x, 2 * gridDim.x, p.tiles_x, p.tiles_y);
+        int s = par;
+        uint32_t sph = 0;
+        for (int i = par; i < my_tiles; i += 2) {
+            const int b = par;
             const uint32_t bph = ((uint32_t)i >> 1) & 1u;
             const uint32_t v = (uint32_t)(w.ty & 1);                 // tile-row parity selects the U_4 variant
             mbar_wait(BAR(D1_EMPTY + b), bph ^ 1);
-            mbar_wait(BAR(A0_FULL + b), bph);                       // implies IN_FULL[s] of this tile (S0 ran on it)
+            mbar_wait(BAR(A0_FULL + b), bph);
+            mbar_wait(BAR(IN_FULL + s), sph);
             tc_fence_after();
+            TRACE(4, i);
             const uint32_t d = tmem_base + H4_D1 + b * 64;
             const uint32_t in_lo = LO(in_base + s * HM_IN_BYTES);
             const uint32_t a0 = tmem_base + H4_A0 + b * 16;
             if (leader) {
                 umma_ts_lohi(d, a0, w0_lo, HI64, idesc_kk, 0u);
                 umma_ts_lohi(d, a0 + 8, w0_lo + 2, HI64, idesc_kk, 1u);
+                if (!(p.dbg & 4)) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     umma_ts_lohi(d, tmem_base + H4_U1 + 8 * k, in_lo + ((HM_IN_S0 + k * 2048) >> 4), HI128, idesc_kmn, 1u);
@@ -216,15 +237,18 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
                     umma_ts_lohi(d, tmem_base + H4_U2 + 8 * k, in_lo + ((HM_IN_S0 + HM_IN_P1 + k * 2048) >> 4), HI128, idesc_kmn, 1u);
                 umma_ts_lohi(d, tmem_base + H4_U3, in_lo + ((HM_IN_S0 + HM_IN_P1 + HM_IN_P2) >> 4), HI128, idesc_kmn, 1u);
                 umma_ts_lohi(d, tmem_base + H4_U4 + 8 * v, in_lo + ((HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3) >> 4), HI128, idesc_kmn, 1u);
+                }
                 umma_commit(BAR(IN_EMPTY + s));
                 umma_commit(BAR(A0_EMPTY + b));
                 umma_commit(BAR(D1_FULL + b));
             }
             __syncwarp();
-            if (++s == H4_STAGES) s = 0;
+            TRACE(5, i);
+            s += 2;
+            if (s >= H4_STAGES) { s -= H4_STAGES; sph ^= 1; }
             w.next();
         }
-    } else if (warp == 15) {
+    } else if (warp == 24) {
         // ===================== MMA issuer 2: fc1 (S2), A operand in TMEM =====================
         const bool leader = elect_one();
         const uint32_t idesc_kk = F16 ? make_idesc_f16(128, 64) : make_idesc_bf16(128, 64);
@@ -234,21 +258,22 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1;
             const uint32_t bph = ((uint32_t)i >> 1) & 1u;
-            mbar_wait(BAR(D2_EMPTY + b), bph ^ 1);
+            if (i >= 2) mbar_wait(BAR(D2_EMPTY + (i - 2) % 6), (uint32_t)((i - 2) / 6) & 1u);   // the tile that used D2[b] before
             mbar_wait(BAR(A2_FULL + b), bph);
             tc_fence_after();
+            TRACE(8, i);
             const uint32_t d = tmem_base + H4_D2 + b * 64;
             const uint32_t a2 = tmem_base + H4_A2 + b * 32;
             if (leader) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_ts_lohi(d, a2 + 8 * k, w1_lo + 2 * k, HI128, idesc_kk, k != 0 ? 1u : 0u);
                 umma_commit(BAR(A2_EMPTY + b));
-                umma_commit(BAR(D2_FULL + b));
+                umma_commit(BAR(D2_FULL + i % 6));
             }
             __syncwarp();
         }
     } else if (warp < 4) {
-        // ===================== U_l -> TMEM once; then E0 (D0 -> A0) and E1 (D1 -> A2, two tiles behind), warps 0-3 =====================
+        // ===================== U_l -> TMEM once; then b0 staging and E0 (D0 -> A0), warps 0-3 =====================
         const int q = warp;
         const int r = q * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -278,85 +303,155 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(UFULL));
         }
-        // E1 trails E0 by TWO tiles: S1(i) (9 UMMAs) is issued at the end of iteration i and its accumulator is first
-        // needed in iteration i + 2, so this warp never sits waiting for the tensor pipe between its two roles.
-        for (int it = 0; it <= my_tiles + 1; ++it) {
-            if (it >= 2) {
-                const int i = it - 2, b = i & 1;
-                const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-                mbar_wait(BAR(A2_EMPTY + b), ph ^ 1);              // satisfied long before the accumulator is: off the critical path
-                mbar_wait(BAR(D1_FULL + b), ph);
-                tc_fence_after();
-                uint32_t v[64];
-                tmem_ld32(lane_base + H4_D1 + b * 64, v);
-                tmem_ld32(lane_base + H4_D1 + b * 64 + 32, v + 32);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(D1_EMPTY + b));
-                uint32_t o[32];
+        // E0 only: E1 runs on warps 4-7 and the b0 operand is staged by warps 20-23.  A single warp executes a dependent
+        // instruction stream at ~4 cycles per instruction and every tcgen05.ld / st round trip costs > 100 cycles, so one role per
+        // warp keeps each per-tile loop short (timeline: experiments/trace_head.py).
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i & 1, d = i % H4_D0S;
+            const uint32_t ph = ((uint32_t)i >> 1) & 1u;
+            mbar_wait(BAR(A0_EMPTY + b), ph ^ 1);
+            mbar_wait(BAR(D0_FULL + d), (uint32_t)(i / H4_D0S) & 1u);
+            tc_fence_after();
+            if (q == 0) TRACE(2, i);
+            uint32_t v[32];
+            tmem_ld32(lane_base + H4_D0 + d * 32, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(D0_EMPTY + d));
+            uint32_t o[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = add_relu_pack<F16>(v[2 * j], v[2 * j + 1], p.c_shift0[2 * j], p.c_shift0[2 * j + 1]);
-                tmem_st32(lane_base + H4_A2 + b * 32, o);
+            for (int j = 0; j < 16; ++j) o[j] = add_relu_pack<F16>(v[2 * j], v[2 * j + 1], p.c_shift_sd0[2 * j], p.c_shift_sd0[2 * j + 1]);
+            tmem_st16(lane_base + H4_A0 + b * 16, o);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(A0_FULL + b));
+            if (q == 0) TRACE(3, i);
+        }
+    } else if (warp >= 25) {
+        // ===================== b0 loaders (warps 25-28): the A operand of S0 goes global -> registers -> TMEM =====================
+        // This thread's pixel (tile row r / 16, column r % 16), 16 channels = 32 bytes = two LDG.128.  b0 comes from HBM (0.64 GB per
+        // subject, written by conv_first long before): the loads run three tiles ahead in a register ring, the TMEM stages another three.
+        const int q = (warp - 25) & 3;                               // TMEM lane quarter = warp % 4: warps 25..28 -> 1, 2, 3, 0
+        const int qq = warp & 3;
+        const int r = qq * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(qq * 32) << 16);
+        (void)q;
+        const int pty = r >> 4, ptx = r & 15;
+        TileWalk wb;
+        wb.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+        auto b0_addr = [&]() { return p.b0 + (((size_t)wb.n * p.h + wb.ty * 8 + pty) * p.w + wb.tx * 16 + ptx) * 2; };
+        uint4 ring_lo[3], ring_hi[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            ring_lo[u] = make_uint4(0, 0, 0, 0); ring_hi[u] = ring_lo[u];
+            if (u < my_tiles && !(p.dbg & 8)) { const uint4* g = b0_addr(); ring_lo[u] = __ldg(g); ring_hi[u] = __ldg(g + 1); wb.next(); }
+        }
+        for (int j0 = 0; j0 < my_tiles; j0 += 3) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int j = j0 + u;
+                if (j >= my_tiles) break;
+                const int sb = u;                                    // j % 3
+                mbar_wait(BAR(B0_EMPTY + sb), ((uint32_t)(j / H4_B0S) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t t8[8] = {ring_lo[u].x, ring_lo[u].y, ring_lo[u].z, ring_lo[u].w, ring_hi[u].x, ring_hi[u].y, ring_hi[u].z, ring_hi[u].w};
+                tmem_st8(lane_base + H4_B0 + sb * 8, t8);
+                if (j + 3 < my_tiles && !(p.dbg & 8)) { const uint4* g = b0_addr(); ring_lo[u] = __ldg(g); ring_hi[u] = __ldg(g + 1); wb.next(); }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
-            }
-            if (it < my_tiles) {
-                const int i = it, b = i & 1, d = i % H4_D0S;
-                const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-                mbar_wait(BAR(A0_EMPTY + b), ph ^ 1);              // satisfied long before the accumulator is: off the critical path
-                mbar_wait(BAR(D0_FULL + d), (uint32_t)(i / H4_D0S) & 1u);
-                tc_fence_after();
-                uint32_t v[32];
-                tmem_ld32(lane_base + H4_D0 + d * 32, v);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(D0_EMPTY + d));
-                uint32_t o[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = add_relu_pack<F16>(v[2 * j], v[2 * j + 1], p.c_shift_sd0[2 * j], p.c_shift_sd0[2 * j + 1]);
-                tmem_st16(lane_base + H4_A0 + b * 16, o);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(A0_FULL + b));
+                if (lane == 0) mbar_arrive(BAR(B0_FULL + sb));
             }
         }
-    } else if (warp < 12) {
-        // ===================== E2: FP32 class scores -> labels; warps 4-7 even tiles, warps 8-11 odd tiles =====================
-        const int b = (warp - 4) >> 2;
+    } else if (warp < 8) {
+        // ===================== E1 (D1 -> A2), warps 4-7 =====================
+        const int q = warp & 3;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i & 1;
+            const uint32_t ph = ((uint32_t)i >> 1) & 1u;
+            mbar_wait(BAR(A2_EMPTY + b), ph ^ 1);
+            mbar_wait(BAR(D1_FULL + b), ph);
+            tc_fence_after();
+            if (q == 0) TRACE(6, i);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {                          // 32 accumulator columns at a time (register budget of a 29-warp CTA: 64)
+                uint32_t v[32];
+                tmem_ld32(lane_base + H4_D1 + b * 64 + 32 * hf, v);
+                tmem_ld_wait();
+                if (hf == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(D1_EMPTY + b));
+                }
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = add_relu_pack<F16>(v[2 * j], v[2 * j + 1], p.c_shift0[32 * hf + 2 * j], p.c_shift0[32 * hf + 2 * j + 1]);
+                tmem_st16(lane_base + H4_A2 + b * 32 + 16 * hf, o);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
+            if (q == 0) TRACE(7, i);
+        }
+    } else if (warp < 20) {
+        // ===================== E2: FP32 class scores -> labels; three warp sets (8-11, 12-15, 16-19), tile i -> set i % 3 =====================
+        const int set = (warp - 8) >> 2;
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int ty = r >> 4, tx = r & 15;
         TileWalk w;
-        w.init(blockIdx.x + b * gridDim.x, 2 * gridDim.x, p.tiles_x, p.tiles_y);
-        uint32_t ph = 0;
-        for (int i = b; i < my_tiles; i += 2, ph ^= 1) {
-            mbar_wait(BAR(D2_FULL + b), ph);
+        w.init(blockIdx.x + set * gridDim.x, H4_E2SETS * gridDim.x, p.tiles_x, p.tiles_y);
+        for (int i = set; i < my_tiles; i += H4_E2SETS) {
+            const int b = i & 1;
+            const uint32_t ph = ((uint32_t)i >> 1) & 1u;
+            mbar_wait(BAR(D2_FULL + i % 6), (uint32_t)(i / 6) & 1u);
             tc_fence_after();
+            if (q == 0) TRACE(9, i);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + H4_D2 + b * 64;
-            uint32_t v[64];
-            tmem_ld32(taddr, v);
-            tmem_ld32(taddr + 32, v + 32);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(D2_EMPTY + b));          // D2[b] drained: S2(i + 2) may overwrite it
-            // class scores in FP32 on plain FFMAs whose second operand is a CONSTANT-BANK word (the weights, shifts and
-            // bias travel by value in the kernel parameters): no shared-memory loads and no register-pair packing moves --
-            // the head is bound by shared-memory bandwidth (UMMA operand reads + epilogue stores + TMA writes), so the
-            // epilogue must not add broadcast LDS traffic of its own.
+            // class scores in FP32: relu(d + s) . w = max(d, -s) . w + s . w, and the constant s . w is part of the bias
+            // (host, float64), so an input channel costs one FMNMX and one packed FFMA2 per PAIR of classes; weights,
+            // negated shifts and bias travel by value in the kernel parameters (constant bank / uniform registers).
+            // The accumulator is read in two halves of 32 columns (register budget of a 25-warp CTA: 80).
+            constexpr int NC2 = (NC + 1) / 2;
+            uint64_t lg2[NC2];
+#pragma unroll
+            for (int j = 0; j < NC2; ++j) asm("mov.b64 %0, {%1, %2};" : "=l"(lg2[j]) : "f"(p.c_bias2[2 * j]), "f"(p.c_bias2[2 * j + 1]));
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+                tmem_ld32(taddr + 32 * hf, v);
+                tmem_ld_wait();
+                if (hf == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(D2_EMPTY + i % 6));  // D2[b] drained: S2(i + 2) may overwrite it
+                }
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) {
+                    const int k = 32 * hf + kk;
+                    if (k == 8 && (p.dbg & 1)) break;                                             // experiment: how much of the tile time is E2 issue?
+                    const float f = fmaxf(__uint_as_float(v[kk]), p.c_nshift1[k]);
+                    uint64_t ff;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(ff) : "f"(f));
+#pragma unroll
+                    for (int j = 0; j < NC2; ++j) {
+                        uint64_t wj;
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(wj) : "f"(p.c_wlc[k][2 * j]), "f"(p.c_wlc[k][2 * j + 1]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(lg2[j]) : "l"(ff), "l"(wj));
+                    }
+                }
+            }
             float lg[NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) lg[c] = p.c_bias[c];                                   // -inf for c >= n_class
-#pragma unroll
-            for (int k = 0; k < 64; ++k) {
-                const float f = fmaxf(__uint_as_float(v[k]) + p.c_shift1[k], 0.f);
-#pragma unroll
-                for (int c = 0; c < NC; ++c) lg[c] = fmaf(f, (k & 1) ? p.c_wl2[k >> 1][c].y : p.c_wl2[k >> 1][c].x, lg[c]);
+            for (int j = 0; j < NC2; ++j) {
+                float lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(lg2[j]));
+                lg[2 * j] = lo;
+                if (2 * j + 1 < NC) lg[2 * j + 1] = hi;
             }
             const int n = w.n, y = w.ty * 8 + ty, x = w.tx * 16 + tx;
             float m1 = lg[0], m2 = -INFINITY;
@@ -400,12 +495,13 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
                     }
                 }
             }
+            if (q == 0) TRACE(10, i);
             w.next();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 15) {
+    if (warp == 24) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

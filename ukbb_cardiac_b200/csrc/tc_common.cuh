@@ -43,6 +43,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
+#ifdef UKBB_MBAR_HINT
         asm volatile(
             "{\n"
             ".reg .pred P1;\n"
@@ -52,7 +53,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(20000u)     // suspend-time hint (ns): sleep in hardware instead of re-issuing the probe
             : "memory");
-        if (!done && spins > (1u << 22)) {
+#else
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+#endif
+        if (!done && spins > (1u << 20)) {
 #ifdef UKBB_DEBUG_MBAR
             printf("mbar timeout: bar %x parity %u block %d thread %d\n", bar, parity, (int)blockIdx.x, (int)threadIdx.x);
 #endif
