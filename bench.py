@@ -29,6 +29,12 @@ sys.path.insert(0, ROOT)
 
 SA = (192, 208, 10, 50)
 FLOP_PER_SLICE = 3.13737216e9          # algorithmic FLOPs, SA 192x208, 4 classes
+# dominant kernel = the fused head (head_ts_kernel, ~30 % of the step): same_dim0 40.89 + 4-tap upsample 40.89 + fc0 817.89 +
+# fc1 327.16 + class scores 20.45 MFLOP per slice by SURVEY 8(d)'s per-layer count
+HEAD_FLOP_PER_SLICE = (40.89 + 40.89 + 817.89 + 327.16 + 20.45) * 1e6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE head_ts_kernel launch (500 slices) from the ncu --set full capture
+# summarised in profiles/r1_ncu_head_ts_summary.txt (a number taken under the profiler is evidence, not a bench value)
+HEAD_DRAM_BYTES_PER_LAUNCH = 1.511e9
 POOL = 8                               # distinct synthetic subjects cycled through a batch
 
 
@@ -212,10 +218,14 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_device()
+    eng.kernel_timer(True)
+    eng.kernel_timer_read()
     l0 = eng.launch_count
     sampler = ClockSampler(local)
     sampler.start()
     ms_dev = timed(step_device, args.steps, record=True)
+    head_ms, head_n = eng.kernel_timer_read()
+    eng.kernel_timer(False)
     launches = eng.launch_count - l0
     for _ in range(max(args.warmup, 3)):
         step_e2e()
@@ -230,13 +240,28 @@ def main():
     e2e_value = slices / (ms_e2e * 1e-3)
     fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / max(len(fwd_ev), 1)        # per 500-slice forward
     peaks = measured_peaks()
-    achieved_tf = FLOP_PER_SLICE * Z * T / (fwd_ms * 1e-3) / 1e12
+    fwd_tf = FLOP_PER_SLICE * Z * T / (fwd_ms * 1e-3) / 1e12
     peak_tf = peaks["bf16_sustained"]
-    roofline = {"bound": "tensor", "kernel": "build_FCN forward (all conv launches of one 500-slice subject)",
-                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16, of measured)",
-                "frac_of_burst": achieved_tf / peaks["bf16_burst"], "frac_of_nominal_2250": achieved_tf / 2250.0,
-                "algorithmic_flop_per_slice": FLOP_PER_SLICE, "avg_forward_ms_per_subject": fwd_ms}
+    if head_n > 0 and args.mode != "fp32":
+        head_avg_ms = head_ms / head_n
+        achieved_tf = HEAD_FLOP_PER_SLICE * Z * T / (head_avg_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "head_ts_kernel (same_dim0 + upsample + fc0 + fc1 + class scores + softmax/argmax/crop; 1 launch per subject)",
+                    "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                    "traffic": HEAD_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (ncu dram read + write)",
+                    "algorithmic_flop_per_launch": HEAD_FLOP_PER_SLICE * Z * T, "avg_launch_ms": head_avg_ms, "launches_timed": head_n,
+                    "timing": "CUDA events on the launching stream around every launch inside the timed region",
+                    "peak_source": peaks["source"] + " (sustained bf16: the kernel runs inside a long step)",
+                    "frac_of_burst": achieved_tf / peaks["bf16_burst"], "frac_of_nominal_2250": achieved_tf / 2250.0,
+                    "share_of_forward": head_avg_ms / fwd_ms,
+                    "whole_forward": {"achieved": fwd_tf, "frac": fwd_tf / peak_tf, "frac_of_burst": fwd_tf / peaks["bf16_burst"],
+                                      "frac_of_nominal_2250": fwd_tf / 2250.0, "algorithmic_flop_per_slice": FLOP_PER_SLICE,
+                                      "avg_forward_ms_per_subject": fwd_ms}}
+    else:
+        roofline = {"bound": "tensor", "kernel": "build_FCN forward (all conv launches of one 500-slice subject)",
+                    "achieved": fwd_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": fwd_tf / peak_tf,
+                    "traffic": None, "peak_source": peaks["source"] + " (sustained bf16, of measured)",
+                    "frac_of_burst": fwd_tf / peaks["bf16_burst"], "frac_of_nominal_2250": fwd_tf / 2250.0,
+                    "algorithmic_flop_per_slice": FLOP_PER_SLICE, "avg_forward_ms_per_subject": fwd_ms}
 
     line = None
     if rank == 0:

@@ -1,0 +1,38 @@
+"""SASS evidence per kernel of libukbb_fcn.so: tcgen05 (UTCHMMA / UTCBAR / LDTM / STTM), TMA (UTMALDG / UTMASTG), mbarrier
+(SYNCS) and packed-FP32 mnemonics, from `cuobjdump -sass`.  usage: sass_summary.py all.sass [out_dir]
+Writes a table to stdout and, with out_dir, the full listing of the kernels on the default BF16 path (gzip)."""
+import collections, gzip, re, sys
+path = sys.argv[1]
+out_dir = sys.argv[2] if len(sys.argv) > 2 else None
+KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "FFMA2", "FADD2", "F2FP", "LDG", "STG", "LDS", "STS", "REDG"]
+DEFAULT = ["conv_first_kernelILb0", "conv_group_kernelILi16ELi32ELi2ELb0", "conv_group_kernelILi32ELi32ELi1ELb0", "conv_group_kernelILi32ELi64ELi2ELb0",
+           "conv_group_kernelILi64ELi64ELi1ELb0", "conv_tc_kernelILi64ELi128ELb0", "conv_tc_kernelILi64ELi256ELb0",
+           "conv_halo_kernelILi64ELi128ELb0ELi0ELb0", "conv_halo_kernelILi64ELi256ELb0ELi0ELb0", "side_tc_kernelILb0", "head_ts_kernelILi4ELb0",
+           "sel_hist0", "sel_histn", "sel_scan", "sel_final", "sel_init", "rescale_pad"]
+cur, funcs = None, collections.OrderedDict()
+for line in open(path, errors="replace"):
+    m = re.search(r"Function : (\S+)", line)
+    if m:
+        cur = m.group(1); funcs[cur] = []
+    elif cur is not None:
+        funcs[cur].append(line)
+print("%-78s %6s " % ("kernel (mangled)", "instr") + " ".join("%7s" % k for k in KEYS))
+for name, lines in funcs.items():
+    ops = collections.Counter()
+    n = 0
+    for l in lines:
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
+        if not m:
+            continue
+        n += 1
+        op = m.group(1)
+        for k in KEYS:
+            if op.startswith(k):
+                ops[k] += 1
+    print("%-78s %6d " % (name[:78], n) + " ".join("%7d" % ops[k] for k in KEYS))
+if out_dir:
+    with gzip.open(out_dir + "/r1_sass_default_path_kernels.txt.gz", "wt") as f:
+        for name, lines in funcs.items():
+            if any(d in name for d in DEFAULT):
+                f.write("Function : %s\n" % name)
+                f.writelines(lines)

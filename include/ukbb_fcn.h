@@ -132,6 +132,13 @@ int ukbb_fcn_sync(ukbb_fcn* h);
 int ukbb_fcn_debug_conv(ukbb_fcn* h, int layer, const void* in_bf16, int n, int hi, int wi, int level_out,
                         void* out_bf16, void* stream);
 
+/* Kernel timer used by bench.py for the roofline line: when enabled, every launch of the fused head kernel
+ * (the dominant kernel of the forward) is bracketed by CUDA events on the launching stream.
+ * ukbb_fcn_kernel_timer_read synchronises the device, returns the summed duration (ms) and the number of
+ * launches recorded since the last read, and clears the list. */
+int ukbb_fcn_kernel_timer(ukbb_fcn* h, int enable);
+int ukbb_fcn_kernel_timer_read(ukbb_fcn* h, double* total_ms, long long* launches);
+
 /* Introspection used by bench.py: kernels launched by this handle since creation. */
 long long ukbb_fcn_launch_count(const ukbb_fcn* h);
 int ukbb_fcn_mode(const ukbb_fcn* h);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "ukbb_fcn_sync": (C.c_int, [C.c_void_p]),
     "ukbb_fcn_debug_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p]),
+    "ukbb_fcn_kernel_timer": (C.c_int, [C.c_void_p, C.c_int]),
+    "ukbb_fcn_kernel_timer_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ukbb_fcn_launch_count": (C.c_longlong, [C.c_void_p]),
     "ukbb_fcn_mode": (C.c_int, [C.c_void_p]),
     "ukbb_fcn_n_class": (C.c_int, [C.c_void_p]),

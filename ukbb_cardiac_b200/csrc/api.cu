@@ -370,6 +370,31 @@ int ukbb_fcn_debug_conv(ukbb_fcn* hh, int layer, const void* in_bf16, int n, int
     return debug_conv_bf16(h, layer, in_bf16, n, hi, wi, level_out, out_bf16, (cudaStream_t)stream);
 }
 
+int ukbb_fcn_kernel_timer(ukbb_fcn* hh, int enable) {
+    ukbb::Engine* h = reinterpret_cast<ukbb::Engine*>(hh);
+    if (!h) { ukbb::set_error("kernel_timer: null handle"); return UKBB_E_INVALID; }
+    h->ktimer = enable != 0;
+    return UKBB_OK;
+}
+
+int ukbb_fcn_kernel_timer_read(ukbb_fcn* hh, double* total_ms, long long* launches) {
+    ukbb::Engine* h = reinterpret_cast<ukbb::Engine*>(hh);
+    if (!h || !total_ms || !launches) { ukbb::set_error("kernel_timer_read: null argument"); return UKBB_E_INVALID; }
+    UKBB_CUDA(cudaSetDevice(h->device));
+    UKBB_CUDA(cudaDeviceSynchronize());
+    double ms = 0.0;
+    for (auto& e : h->ktimer_ev) {
+        float t = 0.f;
+        UKBB_CUDA(cudaEventElapsedTime(&t, e.first, e.second));
+        ms += t;
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    *total_ms = ms;
+    *launches = (long long)h->ktimer_ev.size();
+    h->ktimer_ev.clear();
+    return UKBB_OK;
+}
+
 long long ukbb_fcn_launch_count(const ukbb_fcn* hh) { return hh ? reinterpret_cast<const Engine*>(hh)->launches : 0; }
 int ukbb_fcn_mode(const ukbb_fcn* hh) { return hh ? reinterpret_cast<const Engine*>(hh)->mode : -1; }
 int ukbb_fcn_n_class(const ukbb_fcn* hh) { return hh ? reinterpret_cast<const Engine*>(hh)->n_class : -1; }

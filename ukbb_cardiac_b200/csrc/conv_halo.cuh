@@ -143,6 +143,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(tempty(acc), acc_ph ^ 1);
             tc_fence_after();
             const uint32_t d0 = tmem_base + acc * (2 * COUT);
+            // the right 8-column sub-tile of a border tile may lie entirely outside the image (24 columns at level 3 = 1.5 tiles):
+            // its UMMAs are skipped, and so is its epilogue
+            const int nh = ((tile % p.tiles_x) * 16 + 8 < p.wo) ? 2 : 1;
             for (int ch = 0; ch < p.chunks; ++ch) {
                 mbar_wait(a_full(as), aph);
                 tc_fence_after();
@@ -154,6 +157,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
                             for (int h = 0; h < 2; ++h)
+                                if (h < nh)
 #pragma unroll
                                 for (int k = 0; k < CC / 16; ++k)
                                     umma_bf16_lohi(d0 + h * COUT, a_lo + ((((tap / 3) * 18 + (tap % 3) + 8 * h) * RB + k * 32) >> 4), a_hi,
@@ -170,6 +174,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         if (leader) {
 #pragma unroll
                             for (int h = 0; h < 2; ++h)
+                                if (h < nh)
 #pragma unroll
                                 for (int k = 0; k < CC / 16; ++k)
                                     umma_bf16_lohi(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi,
@@ -202,6 +207,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
+                if (x0 + 8 * h >= p.wo) break;                   // sub-tile outside the image: never computed
                 const int ox = x0 + txl + 8 * h;
                 const bool live = oy < p.ho && ox < p.wo;
                 __nv_bfloat16* dst = p.out + (((size_t)n * p.ho + oy) * p.wo + ox) * COUT;

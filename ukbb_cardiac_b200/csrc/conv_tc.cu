@@ -1123,6 +1123,11 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
             hp.logits = logits ? logits + po : nullptr;
             hp.prob = prob ? prob + po : nullptr;
             hp.counts = counts ? counts + (size_t)n0 * h->n_class : nullptr;
+            cudaEvent_t kt0 = nullptr, kt1 = nullptr;
+            if (h->ktimer) {                                        // ukbb_fcn_kernel_timer: events on the launching stream
+                UKBB_CUDA(cudaEventCreate(&kt0)); UKBB_CUDA(cudaEventCreate(&kt1));
+                UKBB_CUDA(cudaEventRecord(kt0, st));
+            }
             switch (h->n_class) {
                 case 2: rc = launch_head<2>(S, hp, h->sms, st); break;
                 case 3: rc = launch_head<3>(S, hp, h->sms, st); break;
@@ -1130,6 +1135,7 @@ int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre
                 case 5: case 6: rc = launch_head<6>(S, hp, h->sms, st); break;
                 default: rc = launch_head<8>(S, hp, h->sms, st); break;
             }
+            if (h->ktimer && !rc) { UKBB_CUDA(cudaEventRecord(kt1, st)); h->ktimer_ev.emplace_back(kt0, kt1); }
             if (rc) return rc;
             h->launches++;
             if ((hp.dbg & 16) && getenv("UKBB_HEAD_TRACE")) {       // experiment: dump the timeline of CTA 0

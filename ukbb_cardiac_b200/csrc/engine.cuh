@@ -1,6 +1,8 @@
 // Engine state behind the opaque ukbb_fcn handle (internal).
 #pragma once
 #include "common.cuh"
+#include <vector>
+#include <utility>
 
 namespace ukbb {
 
@@ -25,6 +27,8 @@ struct Engine {
     unsigned long long* d_counts = nullptr;
     int counts_cap = 0, counts_n = 0;
     long long launches = 0;
+    bool ktimer = false;                                  // ukbb_fcn_kernel_timer
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktimer_ev;
     // whole-subject staging (ukbb_fcn_segment_host): two slots so H2D / compute / D2H overlap
     float* st_vol[2] = {nullptr, nullptr};
     uint8_t* st_labels[2] = {nullptr, nullptr};

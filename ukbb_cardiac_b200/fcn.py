@@ -237,6 +237,17 @@ class FCNEngine:
                                                     out.data_ptr(), self._stream()))
         return out
 
+    def kernel_timer(self, enable: bool) -> None:
+        """Bracket every launch of the fused head kernel with CUDA events on the launching stream (bench.py roofline)."""
+        _lib.check(self.lib.ukbb_fcn_kernel_timer(self._h, 1 if enable else 0))
+
+    def kernel_timer_read(self):
+        """(summed kernel time in ms, launches) since the last read; synchronises the device."""
+        import ctypes as C
+        ms, n = C.c_double(0.0), C.c_longlong(0)
+        _lib.check(self.lib.ukbb_fcn_kernel_timer_read(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ukbb_fcn_launch_count(self._h))
