@@ -19,6 +19,7 @@
 #include "conv_halo.cuh"
 #include "conv_group.cuh"
 #include "conv_first.cuh"
+#include "conv_first_tc.cuh"
 #include "head_fused.cuh"
 #include "head_mma.cuh"
 #include "head_tc.cuh"
@@ -415,7 +416,10 @@ struct Bf16State {
     HeadMmaMaps hm;
     SideMaps sm;                             // side_tc_kernel: same_dim_l + fc0 column block of levels 1..4 in one launch
     int side = 1;
-    int first = 1;                           // conv0_0 + conv0_1 in one launch (conv_first.cuh)
+    int first = 2;                           // conv0_0 + conv0_1 in one launch: 1 = conv0_0 in FP32 on the CUDA cores (conv_first.cuh),
+                                             // 2 = conv0_0 on the tensor pipe, hi/lo split of the FP32 image (conv_first_tc.cuh)
+    __nv_bfloat16* wb0 = nullptr;            // conv_first_tc: expanded conv0_0 weights [64][64]
+    CUtensorMap map_b0;
 };
 
 static CUtensorMapSwizzle swizzle_for(int cc) {
@@ -630,7 +634,7 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
     S->fp16 = h->mode == UKBB_MODE_FP16 ? 1 : 0;
     S->fused_head = getenv("UKBB_NO_FUSED_HEAD") ? 0 : (getenv("UKBB_HEAD_GATHER") ? 1 : (getenv("UKBB_HEAD_V2") ? 2 : (getenv("UKBB_HEAD_V3") ? 3 : 4)));
     S->side = (S->fused_head >= 3 && !getenv("UKBB_NO_SIDE")) ? 1 : 0;
-    S->first = getenv("UKBB_NO_FIRST") ? 0 : 1;
+    S->first = getenv("UKBB_NO_FIRST") ? 0 : (getenv("UKBB_FIRST_FP32") ? 1 : 2);
     {   // class-score layer of head_tc: FP32 weights [k][8] and bias, passed by value (constant bank)
         const ukbb_conv_weights& c = w->conv[UKBB_N_CONV - 1];
         for (int k = 0; k < 64; ++k)
@@ -645,6 +649,38 @@ int bf16_prepare(Engine* h, const ukbb_fcn_weights* w) {
             for (int dy = 0; dy < 3; ++dy)
                 for (int dx = 0; dx < 3; ++dx) S->c0.w[dy * 3 + dx][co] = (float)((double)c.kernel[(size_t)(dx * 3 + dy) * 16 + co] * sc);
         }
+    }
+    {   // conv_first_tc: B0[n = pixel s * 16 + co][k = part * 18 + row r * 6 + column c] = w_hi | w_hi | w_lo of tap (r, kx = c - s)
+        std::vector<__nv_bfloat16> b0(64 * 64);
+        auto r16 = [&](float v, float* back) {
+            __nv_bfloat16 out;
+            if (S->fp16) { const __half hv = __float2half_rn(v); memcpy(&out, &hv, 2); *back = __half2float(hv); }
+            else { out = __float2bfloat16(v); *back = __bfloat162float(out); }
+            return out;
+        };
+        for (int sp = 0; sp < 4; ++sp)
+            for (int co = 0; co < 16; ++co)
+                for (int k = 0; k < 64; ++k) {
+                    float dummy;
+                    __nv_bfloat16 val = r16(0.f, &dummy);
+                    if (k < 54) {
+                        const int part = k / 18, r = (k % 18) / 6, c = k % 6, kx = c - sp;
+                        if (kx >= 0 && kx <= 2) {
+                            const float wv = S->c0.w[r * 3 + kx][co];
+                            float hi_f, lo_f;
+                            const __nv_bfloat16 hi = r16(wv, &hi_f);
+                            const __nv_bfloat16 lo = r16(wv - hi_f, &lo_f);
+                            val = part < 2 ? hi : lo;
+                        }
+                    }
+                    b0[(size_t)(sp * 16 + co) * 64 + k] = val;
+                }
+        UKBB_CUDA(cudaMalloc(&S->wb0, b0.size() * 2));
+        UKBB_CUDA(cudaMemcpy(S->wb0, b0.data(), b0.size() * 2, cudaMemcpyHostToDevice));
+        cuuint64_t d[2] = {64, 64}; cuuint64_t st1[1] = {128}; cuuint32_t bx[2] = {64, 64}; cuuint32_t e2[2] = {1, 1};
+        CUresult r = S->encode(&S->map_b0, S->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, S->wb0, d, st1, bx, e2,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(conv0_0 weights) failed: %d", (int)r); return UKBB_E_CUDA; }
     }
     for (int li : {13, 18, 19}) {          // 1x1 layers of the head: fold gamma / sqrt(var + eps) into the weights (head_tc.cuh)
         const ukbb_conv_weights& c = w->conv[li];
@@ -740,7 +776,7 @@ void bf16_release(Engine* h) {
     for (int i = 0; i < UKBB_N_CONV; ++i) { cudaFree(S->w[i]); cudaFree(S->wg[i]); }
     cudaFree(S->cat); cudaFree(S->f0); cudaFree(S->f1);
     for (int l = 0; l < 5; ++l) { cudaFree(S->t[l]); cudaFree(S->u[l]); }
-    cudaFree(S->ones);
+    cudaFree(S->ones); cudaFree(S->wb0);
     for (int i = 0; i < UKBB_N_CONV; ++i) cudaFree(S->wf[i]);
     delete S;
     h->tc = nullptr;
@@ -987,6 +1023,16 @@ static int launch_first2(const Bf16State* S, const TcLayerPlan& P1, const CUtens
     memcpy(fp.w0, S->c0.w, sizeof(fp.w0));
     memcpy(fp.shift0, S->c0.shift, sizeof(fp.shift0));
     const int grid = fp.n_tiles < sms ? fp.n_tiles : sms;
+    if (S->first == 2) {
+        using CfgT = ConvFirstTcCfg;
+        static bool attr_set_tc = false;
+        if (!attr_set_tc) {
+            UKBB_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::SMEM_BYTES));
+            attr_set_tc = true;
+        }
+        UKBB_CUDA(launch_pdl(conv_first_tc_kernel<F16>, grid, CfgT::THREADS, CfgT::SMEM_BYTES, st, map_img, P1.map_b, S->map_b0, P1.map_out, fp));
+        return UKBB_OK;
+    }
     UKBB_CUDA(launch_pdl(conv_first_kernel<F16>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, map_img, P1.map_b, P1.map_out, fp));
     return UKBB_OK;
 }
