@@ -183,18 +183,36 @@ def main():
         torch.cuda.synchronize(dev)
 
     fwd_ev = []
+    # device-resident path: the percentile rescale of subject s + 1 runs on a side stream while the forward of subject s runs
+    # on the main stream (two padded buffers), as ukbb_fcn_segment_host does internally for host buffers
+    pre_stream = torch.cuda.Stream(dev)
+    x2, y2 = (X + 15) // 16 * 16, (Y + 15) // 16 * 16
+    pad = [torch.empty((Z * T, y2, x2), dtype=torch.float32, device=dev) for _ in range(2)]
+    vv = [torch.empty(2, dtype=torch.float64, device=dev) for _ in range(2)]
+    ev_pre = [torch.cuda.Event() for _ in range(2)]
+    ev_fwd = [torch.cuda.Event() for _ in range(2)]
 
     def step_device(record=False):
-        for s in range(S):
-            vol = dev_pool[s % pool]
-            padded, vlvh, (xp, yp) = eng.preprocess(vol, Z * T, X, Y)
-            if record:
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-            eng.forward(padded, xp, yp, X, Y)
-            if record:
-                e1.record(stream)
-                fwd_ev.append((e0, e1))
+        xp = yp = 0
+        pre_stream.wait_stream(stream)
+        for s in range(S + 1):
+            if s < S:
+                slot = s & 1
+                with torch.cuda.stream(pre_stream):
+                    pre_stream.wait_event(ev_fwd[slot])              # the forward that read pad[slot] two subjects ago
+                    _, _, (xp, yp) = eng.preprocess(dev_pool[s % pool], Z * T, X, Y, out=pad[slot], vlvh=vv[slot])
+                    ev_pre[slot].record(pre_stream)
+            if s >= 1:
+                slot = (s - 1) & 1
+                stream.wait_event(ev_pre[slot])
+                if record:
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                eng.forward(pad[slot], xp, yp, X, Y)
+                if record:
+                    e1.record(stream)
+                    fwd_ev.append((e0, e1))
+                ev_fwd[slot].record(stream)
 
     def step_e2e():
         for s in range(S):
@@ -281,6 +299,7 @@ def main():
             "config": {"workload": "%d synthetic SA subjects (192x208x10x50, 500 slices each) per GPU per step" % S,
                        "subjects_per_gpu": S, "global_subjects": S * world, "mode": args.mode, "n_class": 4,
                        "l2_policy": "inputs larger than L2: %d distinct 80 MB volumes cycled" % pool,
+                       "pipeline": "rescale of subject s+1 on a side stream overlaps the forward of subject s",
                        "weights": "random-init (seed 0), reference TF checkpoint layout", "parallelism": "dp%d" % world},
             "subjects_per_s": value / (Z * T),
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": S * nvox * 4,

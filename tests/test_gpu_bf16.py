@@ -255,3 +255,23 @@ def test_first_tc_kernel_matches_fp32_conv0(monkeypatch, mode, shape):
     rel = float((g1 - g2).abs().max() / g2.abs().max())
     assert rel < (0.04 if mode == "bf16" else 0.006), rel
     assert float((l1 == l2).float().mean()) >= (0.985 if mode == "bf16" else 0.997)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(3, 64, 96), (5, 208, 192), (7, 48, 80), (1, 32, 48)])
+def test_cluster_multicast_bit_identical(monkeypatch, mode, shape):
+    """Levels 3 / 4 (conv_halo_kernel, streamed weights): clusters of two CTAs fetch every weight tile once and multicast it to
+    both shared memories; the arithmetic per tile is unchanged, so logits and labels are bit-identical to the single-CTA
+    launches -- including odd tile counts, where the second CTA of the last pair walks the weight stream on a dummy tile."""
+    w = synth.make_weights(0, 4)
+    img = np.random.default_rng(shape[0]).random(shape + (1,)).astype(np.float32)
+    dev = to_device_layout(img)
+    with FCNEngine(w, mode=mode) as eng:
+        l1, g1, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+    monkeypatch.setenv("UKBB_NO_CLUSTER", "1")
+    with FCNEngine(w, mode=mode) as eng:
+        l2, g2, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+    assert torch.equal(g1, g2)
+    assert torch.equal(l1, l2)

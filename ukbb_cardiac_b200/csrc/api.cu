@@ -230,10 +230,12 @@ int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode
     if (!rc) {
         cudaError_t e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_pre, cudaStreamNonBlocking);
         for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
             e = cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_compute[s], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_d2h[s], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pre[s], cudaEventDisableTiming);
         }
         if (e != cudaSuccess) { set_error("create: stream/event creation failed: %s", cudaGetErrorString(e)); rc = UKBB_E_CUDA; }
     }
@@ -260,10 +262,12 @@ void ukbb_fcn_destroy(ukbb_fcn* hh) {
         if (h->ev_h2d[s]) cudaEventDestroy(h->ev_h2d[s]);
         if (h->ev_compute[s]) cudaEventDestroy(h->ev_compute[s]);
         if (h->ev_d2h[s]) cudaEventDestroy(h->ev_d2h[s]);
+        if (h->ev_pre[s]) cudaEventDestroy(h->ev_pre[s]);
+        cudaFree(h->st_pad[s]);
     }
-    cudaFree(h->st_pad);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->s_pre) cudaStreamDestroy(h->s_pre);
     delete h;
 }
 
@@ -315,22 +319,28 @@ int ukbb_fcn_segment_host(ukbb_fcn* hh, const float* vol, int x, int y, int z, i
         if (!h->st_vlvh[slot]) UKBB_CUDA(cudaMalloc(&h->st_vlvh[slot], 2 * sizeof(double)));
         h->st_cap[slot] = vox;
     }
-    if (h->st_pad_cap < padvox) {
+    if (h->st_pad_cap[slot] < padvox) {
         UKBB_CUDA(cudaDeviceSynchronize());
-        cudaFree(h->st_pad); h->st_pad = nullptr; h->st_pad_cap = 0;
-        UKBB_CUDA(cudaMalloc(&h->st_pad, padvox * sizeof(float)));
-        h->st_pad_cap = padvox;
+        cudaFree(h->st_pad[slot]); h->st_pad[slot] = nullptr; h->st_pad_cap[slot] = 0;
+        UKBB_CUDA(cudaMalloc(&h->st_pad[slot], padvox * sizeof(float)));
+        h->st_pad_cap[slot] = padvox;
     }
-    // H2D once the previous occupant of this slot has been consumed by the compute stream
-    UKBB_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_compute[slot], 0));
+    // H2D once the previous occupant of this slot's raw volume has been preprocessed
+    UKBB_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_pre[slot], 0));
     UKBB_CUDA(cudaMemcpyAsync(h->st_vol[slot], vol, vox * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
     UKBB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
-    UKBB_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[slot], 0));
-    UKBB_CUDA(cudaStreamWaitEvent(st, h->ev_d2h[slot], 0));      // label staging of this slot drained
-    int rc = launch_preprocess(h->pre, h->st_vol[slot], n, x, y, q_lo, q_hi, x2, y2, x_pre, y_pre, h->st_pad,
-                               h->st_vlvh[slot], 0, st, &h->launches);
+    // preprocessing on its own stream (calls are serialised there: one selection workspace per handle); it may run while the
+    // caller's stream is still busy with the forward of the previous subject (other slot)
+    UKBB_CUDA(cudaStreamWaitEvent(h->s_pre, h->ev_h2d[slot], 0));
+    UKBB_CUDA(cudaStreamWaitEvent(h->s_pre, h->ev_compute[slot], 0));    // forward of this slot's previous occupant has read st_pad[slot]
+    UKBB_CUDA(cudaStreamWaitEvent(h->s_pre, h->ev_d2h[slot], 0));        // ... and its (vl, vh) have been read back
+    int rc = launch_preprocess(h->pre, h->st_vol[slot], n, x, y, q_lo, q_hi, x2, y2, x_pre, y_pre, h->st_pad[slot],
+                               h->st_vlvh[slot], 0, h->s_pre, &h->launches);
     if (rc) return rc;
-    rc = forward_any(h, h->st_pad, (int)n, x2, y2, x_pre, y_pre, x, y, h->st_labels[slot], nullptr, nullptr, st);
+    UKBB_CUDA(cudaEventRecord(h->ev_pre[slot], h->s_pre));
+    UKBB_CUDA(cudaStreamWaitEvent(st, h->ev_pre[slot], 0));
+    UKBB_CUDA(cudaStreamWaitEvent(st, h->ev_d2h[slot], 0));      // label staging of this slot drained
+    rc = forward_any(h, h->st_pad[slot], (int)n, x2, y2, x_pre, y_pre, x, y, h->st_labels[slot], nullptr, nullptr, st);
     if (rc) return rc;
     if (counts)
         UKBB_CUDA(cudaMemcpyAsync(h->st_counts[slot], h->d_counts, (size_t)n * h->n_class * sizeof(long long),

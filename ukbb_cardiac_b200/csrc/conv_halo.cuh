@@ -46,7 +46,12 @@ struct ConvHaloCfg {
     static_assert(A_STAGES >= 2, "need at least two patch stages");
 };
 
-template <int CC, int COUT, bool RESIDENT, int NKB, bool F16>
+// CL = true (streamed weights only): the kernel runs in clusters of two CTAs that walk the same (chunk, tap) weight sequence on two
+// different tiles.  Every weight tile is fetched from L2 ONCE per cluster -- the CTA whose rank equals the tile's parity issues a TMA
+// multicast that lands at the same shared-memory offset in both CTAs and signals both b_full barriers -- and a ring slot is refilled
+// only after BOTH tensor pipes have consumed it (tcgen05.commit multicast on both b_empty barriers, count 2).  The level-3/4 layers
+// stream 0.29 / 1.18 MB of weights per 16x16-pixel tile and ran at the L2 roofline (6.7 TB/s of L2 reads).
+template <int CC, int COUT, bool RESIDENT, int NKB, bool F16, bool CL = false>
 __global__ void __launch_bounds__(256, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const ConvHaloParams p) {
@@ -76,7 +81,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < AST; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CL ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
         mbar_init(wfull, 1);
         fence_barrier_init();
@@ -93,6 +98,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (warp != 0) griddep_wait();                       // the producer waits after it has issued the weight loads
     const int tiles_per_slice = p.tiles_x * p.tiles_y;
+    // tile walk: plain round-robin, or (CL) pairs of tiles dealt to clusters; the odd CTA of the last pair may get a tile beyond
+    // n_tiles: it still walks the weight stream (TMA zero-fills its patch, its epilogue stores nothing)
+    const uint32_t crank = CL ? cluster_ctarank() : 0u;
+    const int tile_first = CL ? 2 * ((int)blockIdx.x >> 1) + (int)crank : (int)blockIdx.x;
+    const int tile_step = CL ? ((int)gridDim.x >> 1) * 2 : (int)gridDim.x;
+    const int tile_end = CL ? ((p.n_tiles + 1) >> 1) * 2 : p.n_tiles;
+    if (CL) cluster_sync();                              // both CTAs' barriers are initialised before any remote arrive / multicast
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -107,7 +119,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             griddep_wait();
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            int bt = 0;                                  // running weight-tile index (same sequence in both CTAs of a cluster)
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
                 const int n = tile / tiles_per_slice, t2 = tile - n * tiles_per_slice;
                 const int y0 = (t2 / p.tiles_x) * 16, x0 = (t2 % p.tiles_x) * 16;
                 for (int ch = 0; ch < p.chunks; ++ch) {
@@ -119,7 +132,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(b_empty(bs), bph ^ 1);
                             mbar_arrive_expect_tx(b_full(bs), COUT * RB);
-                            tma_load_2d(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tap * p.cin + ch * CC, 0);
+                            if (!CL) tma_load_2d(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tap * p.cin + ch * CC, 0);
+                            else if ((uint32_t)(bt & 1) == crank) tma_load_2d_mc(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tap * p.cin + ch * CC, 0, (uint16_t)3);
+                            ++bt;
                             if (++bs == BST) { bs = 0; bph ^= 1; }
                         }
                     }
@@ -139,7 +154,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (RESIDENT) { mbar_wait(wfull, 0); tc_fence_after(); }
         int as = 0, bs = 0, acc = 0;
         uint32_t aph = 0, bph = 0, acc_ph = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < tile_end; tile += tile_step) {
             mbar_wait(tempty(acc), acc_ph ^ 1);
             tc_fence_after();
             const uint32_t d0 = tmem_base + acc * (2 * COUT);
@@ -179,7 +194,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 for (int k = 0; k < CC / 16; ++k)
                                     umma_bf16_lohi(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi,
                                                    idesc, (ch | tap | k) != 0 ? 1u : 0u);
-                            umma_commit(b_empty(bs));
+                            if (CL) umma_commit_mc(b_empty(bs), (uint16_t)3); else umma_commit(b_empty(bs));
                         }
                         __syncwarp();
                         if (++bs == BST) { bs = 0; bph ^= 1; }
@@ -200,7 +215,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int ty = r >> 3, txl = r & 7;
         int acc = 0;
         uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < tile_end; tile += tile_step) {
             const int n = tile / tiles_per_slice, t2 = tile - n * tiles_per_slice;
             const int oy = (t2 / p.tiles_x) * 16 + ty, x0 = (t2 % p.tiles_x) * 16;
             mbar_wait(tfull(acc), acc_ph);
@@ -209,7 +224,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int h = 0; h < 2; ++h) {
                 if (x0 + 8 * h >= p.wo) break;                   // sub-tile outside the image: never computed
                 const int ox = x0 + txl + 8 * h;
-                const bool live = oy < p.ho && ox < p.wo;
+                const bool live = oy < p.ho && ox < p.wo && n < p.n;
                 __nv_bfloat16* dst = p.out + (((size_t)n * p.ho + oy) * p.wo + ox) * COUT;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (2 * COUT) + h * COUT;
 #pragma unroll 1
@@ -244,6 +259,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync();                              // the peer may still multicast into this CTA's ring / arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

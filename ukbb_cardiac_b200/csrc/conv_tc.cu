@@ -531,15 +531,24 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
 // Launch with programmatic stream serialization (tc_common.cuh: griddep_launch / griddep_wait): the next kernel's
 // CTAs start their prologue on an SM as soon as the previous kernel's CTA there has exited, instead of after the
 // whole grid has drained.  UKBB_NO_PDL=1 falls back to plain stream order.
-template <typename... KArgs, typename... Args>
+template <int CLUSTER = 1, typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
     static const bool pdl = getenv("UKBB_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (CLUSTER > 1) {                                   // thread-block clusters along x (TMA multicast of shared operands)
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = CLUSTER; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -563,6 +572,20 @@ static int launch_tc(const TcLayerPlan& P, int sms, cudaStream_t st) {
 template <int CC, int COUT, bool RESIDENT, int NKB, bool F16>
 static int launch_halo2(const TcLayerPlan& P, int sms, cudaStream_t st) {
     using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB>;
+    const bool use_cluster = !RESIDENT && getenv("UKBB_NO_CLUSTER") == nullptr;
+    if (!RESIDENT && use_cluster) {
+        // clusters of two CTAs share every weight tile through TMA multicast (conv_halo.cuh)
+        static bool attr_set_cl = false;
+        if (!attr_set_cl) {
+            UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, RESIDENT, NKB, F16, !RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+            attr_set_cl = true;
+        }
+        const int pairs = (P.hp.n_tiles + 1) / 2;
+        const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+        UKBB_CUDA(launch_pdl<2>(conv_halo_kernel<CC, COUT, RESIDENT, NKB, F16, !RESIDENT>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.hp));
+        return UKBB_OK;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, RESIDENT, NKB, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -35,10 +35,11 @@ struct Engine {
     double* st_vlvh[2] = {nullptr, nullptr};
     long long* st_counts[2] = {nullptr, nullptr};
     size_t st_cap[2] = {0, 0};
-    float* st_pad = nullptr;
-    size_t st_pad_cap = 0;
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    float* st_pad[2] = {nullptr, nullptr};               // rescaled + padded volume per slot
+    size_t st_pad_cap[2] = {0, 0};
+    // preprocessing of subject s + 1 (own stream) overlaps the forward of subject s (caller's stream)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_pre = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_pre[2] = {nullptr, nullptr};
 };
 
 // conv_tc.cu: BF16 tcgen05 path

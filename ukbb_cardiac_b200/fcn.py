@@ -124,14 +124,19 @@ class FCNEngine:
         return out
 
     def preprocess(self, vol: torch.Tensor, n_slices: int, x: int, y: int, q: Sequence[float] = (1.0, 99.0),
-                   clip_in_place: bool = False):
+                   clip_in_place: bool = False, out: Optional[torch.Tensor] = None, vlvh: Optional[torch.Tensor] = None):
         """vol: cuda float32 with n_slices*y*x voxels in NIfTI order.  Returns (padded [N, Y2, X2]
-        float32, vl_vh cuda float64[2], (x_pre, y_pre))."""
+        float32, vl_vh cuda float64[2], (x_pre, y_pre)).  `out` / `vlvh` may be passed in to reuse buffers (e.g. when the
+        call runs on a side stream so that it overlaps the forward of the previous subject)."""
         assert vol.is_cuda and vol.dtype == torch.float32 and vol.is_contiguous() and vol.numel() == n_slices * x * y
         x2, x_pre = pad16(x)
         y2, y_pre = pad16(y)
-        out = torch.empty((n_slices, y2, x2), dtype=torch.float32, device=self.device)
-        vlvh = torch.empty(2, dtype=torch.float64, device=self.device)
+        if out is None:
+            out = torch.empty((n_slices, y2, x2), dtype=torch.float32, device=self.device)
+        if vlvh is None:
+            vlvh = torch.empty(2, dtype=torch.float64, device=self.device)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n_slices * y2 * x2
+        assert vlvh.is_cuda and vlvh.dtype == torch.float64 and vlvh.numel() >= 2
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ukbb_fcn_preprocess(
                 self._h, vol.data_ptr(), n_slices, x, y, float(q[0]), float(q[1]), x2, y2, x_pre, y_pre,
