@@ -17,6 +17,7 @@
 // per stage, two stages when they fit (Cout <= 128) so the epilogue overlaps the next tile.
 #pragma once
 #include "tc_common.cuh"
+#include "conv_group.cuh"      // tmem_ld32, bn_relu_pack
 
 namespace ukbb {
 
@@ -35,15 +36,22 @@ struct ConvHaloCfg {
     static constexpr int RB = CC * 2;                                   // bytes per patch row (pixel)
     static constexpr int PATCH_BYTES = (324 * RB + 1023) / 1024 * 1024;
     static constexpr int B_TILE = (COUT * RB + 1023) / 1024 * 1024;
-    static constexpr int B_TILES = RESIDENT ? NKB : (COUT >= 256 ? 3 : 4);
+    // streamed weights: the ring must cover the ~2000-cycle latency of an L2 fetch -- with four 16 KB stages (512 cycles of UMMAs
+    // each) the tensor pipe waited for weights half of the time (7350 cycles per chunk for 3456 cycles of UMMAs); two patch stages
+    // leave room for eight weight stages (Cout = 128) / four 32 KB stages (Cout = 256)
+    static constexpr int A_STREAM = 2;
+    static constexpr int B_FIT = (222 * 1024 - A_STREAM * PATCH_BYTES) / B_TILE;
+    static constexpr int B_TILES = RESIDENT ? NKB : (B_FIT > 8 ? 8 : B_FIT);
     static constexpr int B_BYTES = B_TILES * B_TILE;
     static constexpr int A_MAX = (200 * 1024 - B_BYTES) / PATCH_BYTES;
-    static constexpr int A_STAGES = A_MAX > 4 ? 4 : A_MAX;
+    static constexpr int A_STAGES = RESIDENT ? (A_MAX > 4 ? 4 : A_MAX) : A_STREAM;
     static constexpr int ACC_STAGES = COUT <= 128 ? 2 : 1;
     static constexpr int TMEM_COLS_RAW = ACC_STAGES * 2 * COUT;
     static constexpr int TMEM_COLS = TMEM_COLS_RAW < 32 ? 32 : TMEM_COLS_RAW;  // 64..512, powers of two here
     static constexpr int SMEM_BYTES = A_STAGES * PATCH_BYTES + B_BYTES + 1024 + 512 + 2 * COUT * 4;
     static_assert(A_STAGES >= 2, "need at least two patch stages");
+    static_assert(RESIDENT || B_TILES >= 3, "weight ring too shallow");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 // CL = true (streamed weights only): the kernel runs in clusters of two CTAs that walk the same (chunk, tap) weight sequence on two
@@ -63,15 +71,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_base = smem_base + AST * Cfg::PATCH_BYTES;
     const uint32_t bar_base = b_base + Cfg::B_BYTES;
-    // barriers: a_full[AST] a_empty[AST] b_full[BST] b_empty[BST] tfull[2] tempty[2] wfull
+    // barriers: a_full[AST] a_empty[AST] b_full[8] b_empty[8] tfull[2] tempty[2] wfull
     auto a_full = [&](int s) { return bar_base + 8u * s; };
     auto a_empty = [&](int s) { return bar_base + 8u * (AST + s); };
     auto b_full = [&](int s) { return bar_base + 8u * (2 * AST + s); };
-    auto b_empty = [&](int s) { return bar_base + 8u * (2 * AST + 4 + s); };
-    auto tfull = [&](int a) { return bar_base + 8u * (2 * AST + 8 + a); };
-    auto tempty = [&](int a) { return bar_base + 8u * (2 * AST + 10 + a); };
-    const uint32_t wfull = bar_base + 8u * (2 * AST + 12);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * AST + 13);
+    auto b_empty = [&](int s) { return bar_base + 8u * (2 * AST + 8 + s); };
+    auto tfull = [&](int a) { return bar_base + 8u * (2 * AST + 16 + a); };
+    auto tempty = [&](int a) { return bar_base + 8u * (2 * AST + 18 + a); };
+    const uint32_t wfull = bar_base + 8u * (2 * AST + 20);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * AST + 21);
     const uint32_t ss_base = bar_base + 512;                 // scale[COUT], shift[COUT] as float
     const float* s_scale = reinterpret_cast<const float*>(smem_raw + (ss_base - smem_u32(smem_raw)));
     const float* s_shift = s_scale + COUT;
@@ -81,7 +89,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < AST; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CL ? 2 : 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CL ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
         mbar_init(wfull, 1);
         fence_barrier_init();
@@ -227,6 +235,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const bool live = oy < p.ho && ox < p.wo && n < p.n;
                 __nv_bfloat16* dst = p.out + (((size_t)n * p.ho + oy) * p.wo + ox) * COUT;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (2 * COUT) + h * COUT;
+                if (p.relu && COUT % 64 == 0) {
+                    // 64 accumulator columns per round trip (two tcgen05.ld.x32, one wait), packed FFMA2 + F2FP.RELU, 128 contiguous
+                    // bytes per pixel: the x16 loop below spent ~200 cycles per 16 columns and made the epilogue slower than the UMMAs
+#pragma unroll 1
+                    for (int c = 0; c < COUT; c += 64) {
+                        uint32_t v[64];
+                        tmem_ld32(taddr + c, v);
+                        tmem_ld32(taddr + c + 32, v + 32);
+                        tmem_ld_wait();
+                        uint32_t o[32];
+#pragma unroll
+                        for (int j = 0; j < 64; j += 4) {
+                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + j);
+                            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + j);
+                            o[j / 2] = bn_relu_pack<F16>(v[j], v[j + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                            o[j / 2 + 1] = bn_relu_pack<F16>(v[j + 2], v[j + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                        }
+                        if (live) {
+                            uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll 1
                 for (int c = 0; c < COUT; c += 16) {
                     uint32_t v[16];
