@@ -33,8 +33,8 @@ FLOP_PER_SLICE = 3.13737216e9          # algorithmic FLOPs, SA 1
 # fc1 327.16 + class scores 20.45 MFLOP per slice by SURVEY 8(d)'s per-layer count
 HEAD_FLOP_PER_SLICE = (40.89 + 40.89 + 817.89 + 327.16 + 20.45) * 1e6
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE head_ts_kernel launch (500 slices) from the ncu --set full capture
-# summarised in profiles/r1_ncu_head_ts_summary.txt (a number taken under the profiler is evidence, not a bench value)
-HEAD_DRAM_BYTES_PER_LAUNCH = 1.511e9
+# summarised in profiles/r1_ncu_full_final_summary.txt (a number taken under the profiler is evidence, not a bench value)
+HEAD_DRAM_BYTES_PER_LAUNCH = 1.516e9
 POOL = 8                               # distinct synthetic subjects cycled through a batch
 
 

@@ -5,9 +5,9 @@ import collections, gzip, re, sys
 path = sys.argv[1]
 out_dir = sys.argv[2] if len(sys.argv) > 2 else None
 KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "FFMA2", "FADD2", "F2FP", "LDG", "STG", "LDS", "STS", "REDG"]
-DEFAULT = ["conv_first_kernelILb0", "conv_group_kernelILi16ELi32ELi2ELb0", "conv_group_kernelILi32ELi32ELi1ELb0", "conv_group_kernelILi32ELi64ELi2ELb0",
+DEFAULT = ["conv_first_tc_kernelILb0", "conv_first_kernelILb0", "conv_group_kernelILi16ELi32ELi2ELb0", "conv_group_kernelILi32ELi32ELi1ELb0", "conv_group_kernelILi32ELi64ELi2ELb0",
            "conv_group_kernelILi64ELi64ELi1ELb0", "conv_tc_kernelILi64ELi128ELb0", "conv_tc_kernelILi64ELi256ELb0",
-           "conv_halo_kernelILi64ELi128ELb0ELi0ELb0", "conv_halo_kernelILi64ELi256ELb0ELi0ELb0", "side_tc_kernelILb0", "head_ts_kernelILi4ELb0",
+           "conv_halo_kernelILi64ELi128ELb0ELi0ELb0ELb1", "conv_halo_kernelILi64ELi256ELb0ELi0ELb0ELb1", "side_tc_kernelILb0", "head_ts_kernelILi4ELb0",
            "sel_hist0", "sel_histn", "sel_scan", "sel_final", "sel_init", "rescale_pad"]
 cur, funcs = None, collections.OrderedDict()
 for line in open(path, errors="replace"):
