@@ -191,3 +191,60 @@ def test_error_paths():
     bad = dict(w); bad["conv2d_3/kernel"] = np.zeros((3, 3, 32, 16), np.float32)
     with pytest.raises(ValueError):
         FCNEngine(bad, mode="fp32")
+
+
+def _rescale_oracle(arr):
+    """reference arithmetic (image_utils.py:70-77 under numpy 2) via the oracle restatement; returns (vl, vh, clipped, out)."""
+    a = arr.copy(order="F")
+    out = do.rescale_intensity(a, (1, 99))
+    return do.percentile_linear(arr, 1), do.percentile_linear(arr, 99), a, np.asarray(out, dtype=np.float32)
+
+
+@pytest.mark.parametrize("case", ["int12", "int16_high", "constant", "negative", "fraction", "minus_zero", "int_but_one_65536"])
+def test_preprocess_integer_fast_path_and_fallback(monkeypatch, case):
+    """Integer-valued volumes take the one-pass counting select + lookup-table rescale; anything else (a negative voxel, a
+    fractional one, -0.0, a level above 65535) takes the three-pass radix select on the same call.  Both are bit-exact against
+    the reference arithmetic, and the fast path equals the generic path (UKBB_NO_INT_PATH=1) bit for bit."""
+    rng = np.random.default_rng(11)
+    shape = (37, 29, 3, 5)                                    # odd sizes: pad branches and the n % 4 tail
+    a = np.floor(rng.gamma(2.0, 300.0, size=shape)).astype(np.float32)
+    if case == "int12":
+        a = np.minimum(a, 4095.0)
+    elif case == "int16_high":
+        a = np.minimum(a * 20.0, 65535.0)                     # most levels above the shared-memory histogram
+        a.flat[7] = 65535.0
+    elif case == "constant":
+        a[:] = 123.0
+    elif case == "negative":
+        a.flat[100] = -3.0
+    elif case == "fraction":
+        a.flat[1234] += 0.5
+    elif case == "minus_zero":
+        a.flat[5] = -0.0
+    elif case == "int_but_one_65536":
+        a.flat[9] = 65536.0
+    a = np.asfortranarray(a)
+    x, y = shape[0], shape[1]
+    n_slices = shape[2] * shape[3]
+    w = synth.make_weights(0, 2)
+    results = []
+    for no_int in (False, True):
+        if no_int:
+            monkeypatch.setenv("UKBB_NO_INT_PATH", "1")
+        with FCNEngine(w, mode="fp32") as eng:
+            vol = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))).cuda()
+            out, vlvh, (x_pre, y_pre) = eng.preprocess(vol, n_slices, x, y, clip_in_place=True)
+            torch.cuda.synchronize()
+            results.append((out.cpu().numpy(), vlvh.cpu().numpy(), vol.cpu().numpy()))
+    for k in range(3):
+        np.testing.assert_array_equal(results[0][k], results[1][k])
+    if case == "constant":
+        return                                                # vh == vl: 0 / 0 in the reference too, nothing more to compare
+    vl, vh, clipped, ref = _rescale_oracle(a)
+    o, vv, vol_after = results[0]
+    np.testing.assert_array_equal(vv, np.array([vl, vh]))
+    np.testing.assert_array_equal(vol_after, clipped.reshape(-1, order="F"))
+    x2, _ = pad16(x); y2, _ = pad16(y)
+    exp = np.zeros((n_slices, y2, x2), np.float32)
+    exp[:, y_pre:y_pre + y, x_pre:x_pre + x] = np.transpose(ref.reshape(x, y, n_slices, order="F"), (2, 1, 0))
+    np.testing.assert_array_equal(o, exp)

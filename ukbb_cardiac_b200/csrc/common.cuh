@@ -56,6 +56,7 @@ struct PreprocWorkspace {
     unsigned long long* state = nullptr;  // per-rank prefix / residual rank
     double* vlvh = nullptr;            // device (vl, vh)
     float* sel = nullptr;              // 4 selected order statistics
+    float* lut = nullptr;              // integer fast path: rescaled value per level (65536 + 2)
 };
 int preproc_alloc(PreprocWorkspace& ws);
 void preproc_free(PreprocWorkspace& ws);

@@ -188,7 +188,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                                    (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
                     }
                 } else {
-#pragma unroll 1
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(b_full(bs), bph);
                         tc_fence_after();

@@ -13,8 +13,16 @@
 // read three times for the select and once for the rescale (an SA volume, 80 MB, stays
 // resident in the 126 MB L2 between passes).  HBM-bound integer/byte work: coalesced
 // 128-bit loads, shared-memory histograms, no tensor cores.
+//
+// INTEGER FAST PATH.  DICOM-derived volumes (and the synthetic stacks) are integer valued: when every voxel is an integer in
+// [0, 65535] the four order statistics follow EXACTLY from one 65536-bin counting pass (int_hist_kernel + int_scan_kernel)
+// instead of three radix passes, and the rescale becomes a table lookup (lut_kernel evaluates the reference's double-precision
+// expression once per integer level, so the result is bit-identical to the generic path's per-voxel FP64 division, which is what
+// bounds rescale_pad_kernel on this GPU).  The decision is taken on the device (SelState::nonint / done): the generic kernels
+// are always enqueued and return at once when the fast path has succeeded, so the call stays asynchronous.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace ukbb {
 
@@ -22,11 +30,17 @@ constexpr int NRANK = 4;
 constexpr int BINS0 = 4096, BINS1 = 4096, BINS2 = 256;
 // hist layout: [pass0: 4096][pass1: 4 x 4096][pass2: 4 x 256]
 constexpr int HIST_WORDS = BINS0 + NRANK * BINS1 + NRANK * BINS2;
+constexpr int HIST_INT = HIST_WORDS;       // offset of the 65536-bin integer histogram
 
 struct SelState {                 // device-resident select state
     unsigned long long rank[NRANK];     // residual rank inside the current prefix
     unsigned int prefix[NRANK];         // key prefix resolved so far (12 then 24 then 32 bits)
+    unsigned int nonint;                // set by int_hist_kernel when a voxel is not an integer in [0, 65535]
+    unsigned int done;                  // set by int_scan_kernel: prefix[] already holds the four order statistics
+    unsigned int maxlevel;              // largest integer level seen by int_hist_kernel (bounds the scan)
 };
+constexpr int INT_BINS = 65536, INT_SH = 4096;
+constexpr int LUT_WORDS = INT_BINS + 2;  // [level] -> rescaled value; then the values of voxels clipped to vl / vh
 
 __device__ __forceinline__ unsigned int f2key(float f) {
     const unsigned int u = __float_as_uint(f);
@@ -39,10 +53,104 @@ __device__ __forceinline__ float key2f(unsigned int k) {
 
 __global__ void sel_init_kernel(SelState* st, unsigned int* hist, unsigned long long r0,
                                 unsigned long long r1, unsigned long long r2, unsigned long long r3) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HIST_WORDS; i += gridDim.x * blockDim.x) hist[i] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HIST_WORDS + INT_BINS; i += gridDim.x * blockDim.x) hist[i] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->rank[0] = r0; st->rank[1] = r1; st->rank[2] = r2; st->rank[3] = r3;
         for (int r = 0; r < NRANK; ++r) st->prefix[r] = 0;
+        st->nonint = 0; st->done = 0; st->maxlevel = 0;
+    }
+}
+
+// INTEGER FAST PATH, counting pass: levels below 4096 (all of a 12-bit MR image) go through a shared-memory histogram with the
+// same run folding as pass 0, higher levels straight to global atomics.
+__global__ void __launch_bounds__(512)
+int_hist_kernel(const float* __restrict__ vol, long long n, unsigned int* __restrict__ hist, SelState* __restrict__ st) {
+    __shared__ unsigned int sh[INT_SH];
+    for (int i = threadIdx.x; i < INT_SH; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    unsigned int* h16 = hist + HIST_INT;
+    bool bad = false;
+    int top = 0;
+    auto level = [&](float f) -> int {                       // integer level of the voxel, or -1
+        const int iv = __float2int_rz(f);
+        const bool ok = f >= 0.f && f < 65536.f && (float)iv == f && __float_as_uint(f) != 0x80000000u;
+        bad = bad || !ok;
+        if (ok) top = max(top, iv);
+        return ok ? iv : -1;
+    };
+    auto count = [&](int b, unsigned int c) {
+        if (b < 0) return;
+        if (b < INT_SH) atomicAdd(&sh[b], c); else atomicAdd(&h16[b], c);
+    };
+    const long long n4 = n >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(vol);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(v4 + i);
+        const int b0 = level(v.x), b1 = level(v.y), b2 = level(v.z), b3 = level(v.w);
+        if (b0 == b1 && b1 == b2 && b2 == b3) count(b0, 4u);
+        else { count(b0, 1u); count(b1, 1u); count(b2, 1u); count(b3, 1u); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) count(level(vol[(n4 << 2) + threadIdx.x]), 1u);
+    if (bad) st->nonint = 1u;
+    top = __reduce_max_sync(0xffffffffu, top);
+    if ((threadIdx.x & 31) == 0 && top > 0) atomicMax(&st->maxlevel, (unsigned int)top);
+    __syncthreads();
+    for (int i = threadIdx.x; i < INT_SH; i += blockDim.x)
+        if (sh[i]) atomicAdd(&h16[i], sh[i]);
+}
+
+// INTEGER FAST PATH, selection: one 1024-thread block scans the 65536 counters (64 per thread) and finds the level holding each of the
+// four ranks; the levels are stored as float keys in prefix[] exactly where the third radix pass would have left them.
+__global__ void __launch_bounds__(1024)
+int_scan_kernel(SelState* st, const unsigned int* __restrict__ hist) {
+    __shared__ unsigned long long s_scan[1024];
+    if (st->nonint) return;                                  // uniform: the generic passes will run
+    const unsigned int* h = hist + HIST_INT;
+    const int t = threadIdx.x;
+    const int per = (int)(st->maxlevel / 1024u) + 1;        // bins per thread: 4 for a 12-bit image, 64 at most
+    unsigned long long local = 0;
+    for (int i = 0; i < per; ++i) local += h[t * per + i];
+    s_scan[t] = local;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const unsigned long long v = t >= off ? s_scan[t - off] : 0ull;
+        __syncthreads();
+        s_scan[t] += v;
+        __syncthreads();
+    }
+    const unsigned long long incl = s_scan[t], excl = incl - local;
+    for (int r = 0; r < NRANK; ++r) {
+        const unsigned long long want = st->rank[r];
+        if (want >= excl && want < incl) {
+            unsigned long long cum = excl;
+            int b = t * per;
+            for (int i = 0; i < per; ++i) {
+                const unsigned int c = h[t * per + i];
+                if (cum + c > want) { b = t * per + i; break; }
+                cum += c;
+            }
+            st->prefix[r] = f2key((float)b);
+        }
+    }
+    __syncthreads();
+    if (t == 0) st->done = 1u;
+}
+
+// INTEGER FAST PATH, rescale table: the reference's expression (clip against the float64 thresholds, subtract and divide in double,
+// round to float32) evaluated once per integer level -- identical operations, hence identical bits, to rescale_pad_kernel's slow path.
+__global__ void lut_kernel(const SelState* __restrict__ st, const double* __restrict__ vlvh, float* __restrict__ lut) {
+    if (!st->done) return;
+    const double vl = vlvh[0], vh = vlvh[1];
+    const float fl = (float)vl, fh = (float)vh;
+    const double den = vh - vl;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < LUT_WORDS; i += gridDim.x * blockDim.x) {
+        float v = i < INT_BINS ? (float)i : (i == INT_BINS ? fl : fh);
+        if (i < INT_BINS) {
+            if ((double)v < vl) v = fl;
+            if ((double)v > vh) v = fh;
+        }
+        lut[i] = (float)(((double)v - vl) / den);
     }
 }
 
@@ -50,8 +158,9 @@ __global__ void sel_init_kernel(SelState* st, unsigned int* hist, unsigned long 
 // equal bins among its own consecutive voxels before touching shared memory (neighbouring
 // voxels of an MR image mostly share the top 12 key bits).
 __global__ void __launch_bounds__(512)
-sel_hist0_kernel(const float* __restrict__ vol, long long n, unsigned int* __restrict__ hist) {
+sel_hist0_kernel(const float* __restrict__ vol, long long n, unsigned int* __restrict__ hist, const SelState* __restrict__ st) {
     __shared__ unsigned int sh[BINS0];
+    if (st->done) return;                                    // integer fast path succeeded
     for (int i = threadIdx.x; i < BINS0; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const long long n4 = n >> 2;
@@ -79,6 +188,7 @@ template <int PASS>
 __global__ void __launch_bounds__(512)
 sel_histn_kernel(const float* __restrict__ vol, long long n, const SelState* __restrict__ st,
                  unsigned int* __restrict__ hist) {
+    if (st->done) return;                                    // integer fast path succeeded
     unsigned int pre[NRANK];
 #pragma unroll
     for (int r = 0; r < NRANK; ++r) pre[r] = st->prefix[r];
@@ -121,6 +231,7 @@ sel_scan_kernel(SelState* st, const unsigned int* __restrict__ hist) {
     __shared__ unsigned long long s_newrank[NRANK];
     __shared__ unsigned int s_newpre[NRANK];
     const int t = threadIdx.x;
+    if (st->done) return;                                    // integer fast path succeeded (uniform)
     if (t < NRANK) s_pre[t] = st->prefix[t];
     __syncthreads();
     constexpr int bins = PASS == 2 ? BINS2 : BINS0;
@@ -185,38 +296,67 @@ __global__ void sel_final_kernel(const SelState* __restrict__ st, double t_lo, d
 // Rescale + zero-pad: one thread = 4 consecutive output pixels along X of the padded slice.
 __global__ void __launch_bounds__(256)
 rescale_pad_kernel(float* __restrict__ vol, float* __restrict__ out, const double* __restrict__ vlvh,
-                   long long total4, int x, int y, int x2, int y2, int x_pre, int y_pre, int clip_in_place) {
+                   long long total4, int x, int y, int x2, int y2, int x_pre, int y_pre, int clip_in_place,
+                   const SelState* __restrict__ st, const float* __restrict__ lut) {
     const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= total4) return;
     const double vl = vlvh[0], vh = vlvh[1];
     const float fl = (float)vl, fh = (float)vh;     // what `image[image < vl] = vl` stores
     const double den = vh - vl;
-    const int xq = x2 >> 2;
-    const int ox = (int)(i4 % xq) * 4;
-    const int oy = (int)((i4 / xq) % y2);
-    const long long n = i4 / ((long long)xq * y2);
+    // float32-vs-float64 comparisons as float32 comparisons with the same truth table: (double)v < vl  <=>  v < t_lo with t_lo the
+    // smallest float >= vl, and (double)v > vh  <=>  v > t_hi with t_hi the largest float <= vh (FP64 compares per voxel made the
+    // kernel issue-bound)
+    const float t_lo = (double)fl >= vl ? fl : nextafterf(fl, INFINITY);
+    const float t_hi = (double)fh <= vh ? fh : nextafterf(fh, -INFINITY);
+    const bool fast = st->done != 0;                         // integer volume: table lookup instead of an FP64 division per voxel
+    const unsigned int xq = (unsigned int)x2 >> 2;
+    int ox, oy;
+    long long n;
+    if (total4 < (1ll << 31)) {                              // 32-bit index arithmetic (64-bit divisions cost more than the rescale)
+        const unsigned int i = (unsigned int)i4, t = i / xq;
+        ox = (int)(i - t * xq) * 4;
+        const unsigned int nn = t / (unsigned int)y2;
+        oy = (int)(t - nn * (unsigned int)y2);
+        n = nn;
+    } else {
+        ox = (int)(i4 % xq) * 4;
+        oy = (int)((i4 / xq) % y2);
+        n = i4 / ((long long)xq * y2);
+    }
     const int sy = oy - y_pre;
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (sy >= 0 && sy < y) {
         float* row = vol + (n * y + sy) * (long long)x;
+        const int sx0 = ox - x_pre;
+        float vin[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool vec = ((x | x_pre) & 3) == 0 && sx0 >= 0 && sx0 < x;     // the four pixels are one aligned float4 (SA volumes)
+        if (vec) {
+            const float4 q4 = *reinterpret_cast<const float4*>(row + sx0);
+            vin[0] = q4.x; vin[1] = q4.y; vin[2] = q4.z; vin[3] = q4.w;
+        }
+        bool changed = false;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int sx = ox + u - x_pre;
+            const int sx = sx0 + u;
             if (sx >= 0 && sx < x) {
-                float v = row[sx];
+                float v = vec ? vin[u] : row[sx];
                 // comparisons against the float64 thresholds, like numpy's float32-vs-float64 compare
-                if ((double)v < vl) v = fl;
-                if ((double)v > vh) v = fh;
-                if (clip_in_place) row[sx] = v;
-                r[u] = (float)(((double)v - vl) / den);
+                int li = fast ? (int)v : 0;
+                if (v < t_lo) { v = fl; li = INT_BINS; changed = true; }
+                if (v > t_hi) { v = fh; li = INT_BINS + 1; changed = true; }
+                if (clip_in_place && !vec) row[sx] = v;
+                vin[u] = v;
+                r[u] = fast ? __ldg(lut + li) : (float)(((double)v - vl) / den);
             }
         }
+        if (clip_in_place && vec && changed) *reinterpret_cast<float4*>(row + sx0) = make_float4(vin[0], vin[1], vin[2], vin[3]);
     }
     reinterpret_cast<float4*>(out)[i4] = make_float4(r[0], r[1], r[2], r[3]);
 }
 
 int preproc_alloc(PreprocWorkspace& ws) {
-    UKBB_CUDA(cudaMalloc(&ws.hist, HIST_WORDS * sizeof(unsigned int)));
+    UKBB_CUDA(cudaMalloc(&ws.hist, (HIST_WORDS + INT_BINS) * sizeof(unsigned int)));
+    UKBB_CUDA(cudaMalloc(&ws.lut, LUT_WORDS * sizeof(float)));
     UKBB_CUDA(cudaMalloc(&ws.state, sizeof(SelState)));
     UKBB_CUDA(cudaMalloc(&ws.vlvh, 2 * sizeof(double)));
     UKBB_CUDA(cudaMalloc(&ws.sel, NRANK * sizeof(float)));
@@ -224,7 +364,7 @@ int preproc_alloc(PreprocWorkspace& ws) {
 }
 
 void preproc_free(PreprocWorkspace& ws) {
-    cudaFree(ws.hist); cudaFree(ws.state); cudaFree(ws.vlvh); cudaFree(ws.sel);
+    cudaFree(ws.hist); cudaFree(ws.state); cudaFree(ws.vlvh); cudaFree(ws.sel); cudaFree(ws.lut);
     ws = PreprocWorkspace();
 }
 
@@ -256,17 +396,23 @@ int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int hgrid = sms * 4;       // 4 resident 512-thread CTAs per SM
     sel_init_kernel<<<16, 256, 0, st>>>(state, ws.hist, rk[0], rk[1], rk[2], rk[3]);
-    sel_hist0_kernel<<<hgrid, 512, 0, st>>>(vol, n, ws.hist);
+    if (!getenv("UKBB_NO_INT_PATH")) {
+        int_hist_kernel<<<hgrid, 512, 0, st>>>(vol, n, ws.hist, state);
+        int_scan_kernel<<<1, 1024, 0, st>>>(state, ws.hist);
+        if (launches) *launches += 2;
+    }
+    sel_hist0_kernel<<<hgrid, 512, 0, st>>>(vol, n, ws.hist, state);
     sel_scan_kernel<0><<<1, 1024, 0, st>>>(state, ws.hist);
     sel_histn_kernel<1><<<hgrid, 512, 0, st>>>(vol, n, state, ws.hist);
     sel_scan_kernel<1><<<1, 1024, 0, st>>>(state, ws.hist);
     sel_histn_kernel<2><<<hgrid, 512, 0, st>>>(vol, n, state, ws.hist);
     sel_scan_kernel<2><<<1, 1024, 0, st>>>(state, ws.hist);
     sel_final_kernel<<<1, 32, 0, st>>>(state, t[0], t[1], ws.vlvh, ws.sel, vl_vh_out);
+    lut_kernel<<<32, 256, 0, st>>>(state, ws.vlvh, ws.lut);
     const long long total4 = n_slices * y2 * (x2 / 4);
     rescale_pad_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(vol, out, ws.vlvh, total4, x, y, x2, y2,
-                                                                          x_pre, y_pre, clip_in_place);
-    if (launches) *launches += 9;
+                                                                          x_pre, y_pre, clip_in_place, state, ws.lut);
+    if (launches) *launches += 10;
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
 }
