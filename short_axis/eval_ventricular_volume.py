@@ -1,34 +1,46 @@
 #!/usr/bin/env python3
-"""Drop-in for the reference's short_axis/eval_ventricular_volume.py (same flags, same CSV): clinical measures of every
-subject directory that holds sa.nii.gz and seg_sa.nii.gz.  Reads the label volume with the repository's NIfTI reader
-(nibabel is not required) and counts voxels per frame; inside the deploy pipeline the same numbers come from the device
-(`FCNEngine.segment_volume(...)[2]`, `ukbb_cardiac_b200.volumes.ventricular_volumes`)."""
+"""Clinical measures of the short-axis segmentation, one CSV row per subject.
+
+Command line and output are those of the reference's script of the same name (`--data_dir DIR --output_csv FILE`;
+subject folders holding `sa.nii.gz` and `seg_sa.nii.gz`; columns LVEDV ... RVEF), so `demo_pipeline.py` can call it unchanged.
+The arithmetic lives in `ukbb_cardiac_b200.volumes` (shared with the deploy path, where the per-frame class counts come
+from the device instead of a second pass over the label volume); NIfTI files are read with the repository's own reader."""
 import argparse
-import os
+import pathlib
 import sys
 
 import pandas as pd
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REPO = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
 from ukbb_cardiac_b200 import nifti, volumes  # noqa: E402
 
-if __name__ == '__main__':
-    parser = argparse.ArgumentParser()
-    parser.add_argument('--data_dir', metavar='dir_name', default='', required=True)
-    parser.add_argument('--output_csv', metavar='csv_name', default='', required=True)
-    args = parser.parse_args()
 
-    table, processed_list = [], []
-    for data in sorted(os.listdir(args.data_dir)):
-        data_dir = os.path.join(args.data_dir, data)
-        image_name = '{0}/sa.nii.gz'.format(data_dir)
-        seg_name = '{0}/seg_sa.nii.gz'.format(data_dir)
-        if os.path.exists(image_name) and os.path.exists(seg_name):
-            print(data)
-            nim = nifti.load(image_name)
-            seg = nifti.load(seg_name).get_data()
-            val = volumes.ventricular_volumes(volumes.frame_counts_from_labels(seg), nim.header['pixdim'], int(nim.header['dim'][4]))
-            table += [volumes.table_row(val)]
-            processed_list += [data]
-    df = pd.DataFrame(table, index=processed_list, columns=volumes.COLUMNS)
-    df.to_csv(args.output_csv)
+def subject_row(folder: pathlib.Path):
+    """Measures of one subject folder, or None when either file is missing (the reference skips such folders silently)."""
+    image_path, label_path = folder / "sa.nii.gz", folder / "seg_sa.nii.gz"
+    if not (image_path.is_file() and label_path.is_file()):
+        return None
+    header = nifti.load(str(image_path)).header
+    counts = volumes.frame_counts_from_labels(nifti.load(str(label_path)).get_data())
+    return volumes.table_row(volumes.ventricular_volumes(counts, header["pixdim"], int(header["dim"][4])))
+
+
+def main(argv=None) -> int:
+    cli = argparse.ArgumentParser(description=__doc__.splitlines()[0])
+    cli.add_argument("--data_dir", metavar="dir_name", default="", required=True)
+    cli.add_argument("--output_csv", metavar="csv_name", default="", required=True)
+    opts = cli.parse_args(argv)
+    rows, names = [], []
+    for folder in sorted(pathlib.Path(opts.data_dir).iterdir(), key=lambda q: q.name):
+        row = subject_row(folder) if folder.is_dir() else None
+        if row is not None:
+            print(folder.name)
+            rows.append(row)
+            names.append(folder.name)
+    pd.DataFrame(rows, index=names, columns=volumes.COLUMNS).to_csv(opts.output_csv)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
