@@ -143,8 +143,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("UKBB_BENCH_MODE", "bf16"), choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--subjects", type=int, default=None, help="SA subjects per GPU per step (default 256 bf16, 2 fp32)")
-    ap.add_argument("--ref-frames", type=int, default=5)
-    ap.add_argument("--cpu-frames", type=int, default=10, help="frames in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--ref-frames", type=int, default=20, help="frames per step of the reference arm (20 frames = 200 slices, ~5 s of CPU work)")
+    ap.add_argument("--cpu-frames", type=int, default=50, help="frames in the cpu_baseline sample (0 = skip); 50 = one whole subject, ~14 s")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
