@@ -284,7 +284,7 @@ def main():
     line = None
     if rank == 0:
         cpu = None
-        if args.cpu_frames > 0:
+        if args.cpu_frames > 0 and world == 1:               # the CPU baseline is measured at N = 1 only
             threads = os.cpu_count() or 1
             v, dt, n = cpu_reference_sample(args.cpu_frames, threads)
             cpu = {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
