@@ -137,3 +137,27 @@ def test_synth_stack_properties():
     assert np.all(v == np.rint(v)) and v.min() >= 0 and v.max() <= 4095
     np.testing.assert_array_equal(v, synth.make_stack(3, (32, 48, 2, 3)))
     assert not np.array_equal(v, synth.make_stack(4, (32, 48, 2, 3)))
+
+
+def test_parallel_gzip_is_a_plain_gz_stream(tmp_path):
+    """Large volumes are deflated as a multi-member gzip stream by a thread pool; any gzip reader returns the same bytes."""
+    import gzip
+    import time
+    rng = np.random.default_rng(0)
+    vol = np.zeros((96, 104, 10, 50), dtype=np.float64, order="F")            # 40 MB of label-like data (mostly zeros)
+    vol[30:60, 40:70] = rng.integers(0, 4, size=(30, 30, 10, 50))
+    img = nifti.Nifti1Image(vol, np.diag([1.8, 1.8, 10.0, 1.0]))
+    p = str(tmp_path / "seg.nii.gz")
+    t0 = time.perf_counter()
+    nifti.save(img, p)
+    dt = time.perf_counter() - t0
+    raw = open(p, "rb").read()
+    assert raw[:2] == b"\x1f\x8b" and raw.count(b"\x1f\x8b\x08") >= 2     # several members
+    plain = gzip.decompress(raw)                                               # stdlib reader: concatenation of the members
+    assert len(plain) == 352 + vol.nbytes
+    with gzip.open(p, "rb") as g:
+        assert g.read() == plain
+    back = nifti.load(p)
+    np.testing.assert_array_equal(back.get_data(), vol)
+    assert nifti.gzip_parallel(b"abc" * 100) == gzip.compress(b"abc" * 100, compresslevel=1, mtime=0)   # small payload: one member
+    print("saved %d MB in %.2f s" % (vol.nbytes >> 20, dt))
