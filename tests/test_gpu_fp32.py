@@ -200,13 +200,15 @@ def _rescale_oracle(arr):
     return do.percentile_linear(arr, 1), do.percentile_linear(arr, 99), a, np.asarray(out, dtype=np.float32)
 
 
+@pytest.mark.parametrize("shape", [(37, 29, 3, 5), (40, 28, 3, 5), (64, 48, 2, 3)])
 @pytest.mark.parametrize("case", ["int12", "int16_high", "constant", "negative", "fraction", "minus_zero", "int_but_one_65536"])
-def test_preprocess_integer_fast_path_and_fallback(monkeypatch, case):
+def test_preprocess_integer_fast_path_and_fallback(monkeypatch, case, shape):
     """Integer-valued volumes take the one-pass counting select + lookup-table rescale; anything else (a negative voxel, a
     fractional one, -0.0, a level above 65535) takes the three-pass radix select on the same call.  Both are bit-exact against
     the reference arithmetic, and the fast path equals the generic path (UKBB_NO_INT_PATH=1) bit for bit."""
+    # (37, 29): odd sizes, pad branches, n % 4 tail, scalar rescale; (40, 28) and (64, 48): rows of whole float4s (x_pre = 4 / 0),
+    # the table-lookup rescale kernel
     rng = np.random.default_rng(11)
-    shape = (37, 29, 3, 5)                                    # odd sizes: pad branches and the n % 4 tail
     a = np.floor(rng.gamma(2.0, 300.0, size=shape)).astype(np.float32)
     if case == "int12":
         a = np.minimum(a, 4095.0)

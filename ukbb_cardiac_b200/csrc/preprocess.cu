@@ -41,6 +41,8 @@ struct SelState {                 // device-resident select state
 };
 constexpr int INT_BINS = 65536, INT_SH = 4096;
 constexpr int LUT_WORDS = INT_BINS + 2;  // [level] -> rescaled value; then the values of voxels clipped to vl / vh
+constexpr int LUT_THR = LUT_WORDS;       // then t_lo, t_hi (float32 thresholds with the float64 truth table), fl, fh
+constexpr int LUT_ALLOC = LUT_WORDS + 4;
 
 __device__ __forceinline__ unsigned int f2key(float f) {
     const unsigned int u = __float_as_uint(f);
@@ -152,6 +154,41 @@ __global__ void lut_kernel(const SelState* __restrict__ st, const double* __rest
         }
         lut[i] = (float)(((double)v - vl) / den);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        lut[LUT_THR] = (double)fl >= vl ? fl : nextafterf(fl, INFINITY);
+        lut[LUT_THR + 1] = (double)fh <= vh ? fh : nextafterf(fh, -INFINITY);
+        lut[LUT_THR + 2] = fl;
+        lut[LUT_THR + 3] = fh;
+    }
+}
+
+// INTEGER FAST PATH, rescale + zero-pad for rows that are whole float4s (x and x_pre multiples of 4: every SA volume): one thread =
+// one aligned float4 of the padded output, no index divisions (3-D grid), thresholds precomputed, four table lookups.
+__global__ void __launch_bounds__(256)
+rescale_lut_kernel(float* __restrict__ vol, float* __restrict__ out, const SelState* __restrict__ st, const float* __restrict__ lut,
+                   int x, int y, int x2, int y2, int x_pre, int y_pre, int clip_in_place) {
+    if (!st->done) return;                                   // rescale_pad_kernel does the work
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;     // float4 index inside the padded row
+    const int oy = blockIdx.y * blockDim.y + threadIdx.y;
+    const long long n = blockIdx.z;
+    if (q >= (x2 >> 2) || oy >= y2) return;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int sy = oy - y_pre, sx0 = q * 4 - x_pre;
+    if (sy >= 0 && sy < y && sx0 >= 0 && sx0 < x) {
+        const float t_lo = lut[LUT_THR], t_hi = lut[LUT_THR + 1], fl = lut[LUT_THR + 2], fh = lut[LUT_THR + 3];
+        float4* src = reinterpret_cast<float4*>(vol + (n * y + sy) * (long long)x + sx0);
+        float4 v = *src;
+        bool changed = false;
+        auto one = [&](float& f) -> float {
+            int li = (int)f;
+            if (f < t_lo) { f = fl; li = INT_BINS; changed = true; }
+            if (f > t_hi) { f = fh; li = INT_BINS + 1; changed = true; }
+            return __ldg(lut + li);
+        };
+        r.x = one(v.x); r.y = one(v.y); r.z = one(v.z); r.w = one(v.w);
+        if (clip_in_place && changed) *src = v;
+    }
+    reinterpret_cast<float4*>(out)[(n * y2 + oy) * (long long)(x2 >> 2) + q] = r;
 }
 
 // PASS 0: 4096-bin histogram of key >> 20, shared-memory privatised.  Each thread folds runs of
@@ -297,7 +334,8 @@ __global__ void sel_final_kernel(const SelState* __restrict__ st, double t_lo, d
 __global__ void __launch_bounds__(256)
 rescale_pad_kernel(float* __restrict__ vol, float* __restrict__ out, const double* __restrict__ vlvh,
                    long long total4, int x, int y, int x2, int y2, int x_pre, int y_pre, int clip_in_place,
-                   const SelState* __restrict__ st, const float* __restrict__ lut) {
+                   const SelState* __restrict__ st, const float* __restrict__ lut, int lut_kernel_enqueued) {
+    if (lut_kernel_enqueued && st->done) return;             // rescale_lut_kernel has written the output
     const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= total4) return;
     const double vl = vlvh[0], vh = vlvh[1];
@@ -356,7 +394,7 @@ rescale_pad_kernel(float* __restrict__ vol, float* __restrict__ out, const doubl
 
 int preproc_alloc(PreprocWorkspace& ws) {
     UKBB_CUDA(cudaMalloc(&ws.hist, (HIST_WORDS + INT_BINS) * sizeof(unsigned int)));
-    UKBB_CUDA(cudaMalloc(&ws.lut, LUT_WORDS * sizeof(float)));
+    UKBB_CUDA(cudaMalloc(&ws.lut, LUT_ALLOC * sizeof(float)));
     UKBB_CUDA(cudaMalloc(&ws.state, sizeof(SelState)));
     UKBB_CUDA(cudaMalloc(&ws.vlvh, 2 * sizeof(double)));
     UKBB_CUDA(cudaMalloc(&ws.sel, NRANK * sizeof(float)));
@@ -410,8 +448,15 @@ int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int 
     sel_final_kernel<<<1, 32, 0, st>>>(state, t[0], t[1], ws.vlvh, ws.sel, vl_vh_out);
     lut_kernel<<<32, 256, 0, st>>>(state, ws.vlvh, ws.lut);
     const long long total4 = n_slices * y2 * (x2 / 4);
+    const int vec_rows = ((x | x_pre) & 3) == 0 && n_slices <= 65535 && !getenv("UKBB_NO_INT_PATH");
+    if (vec_rows) {
+        const int xq = x2 >> 2, bx = xq >= 64 ? 64 : (xq + 15) / 16 * 16, by = 256 / bx;
+        dim3 block(bx, by), grid((xq + bx - 1) / bx, (y2 + by - 1) / by, (unsigned)n_slices);
+        rescale_lut_kernel<<<grid, block, 0, st>>>(vol, out, state, ws.lut, x, y, x2, y2, x_pre, y_pre, clip_in_place);
+        if (launches) *launches += 1;
+    }
     rescale_pad_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(vol, out, ws.vlvh, total4, x, y, x2, y2,
-                                                                          x_pre, y_pre, clip_in_place, state, ws.lut);
+                                                                          x_pre, y_pre, clip_in_place, state, ws.lut, vec_rows);
     if (launches) *launches += 10;
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
