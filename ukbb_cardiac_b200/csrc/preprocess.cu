@@ -336,8 +336,7 @@ rescale_pad_kernel(float* __restrict__ vol, float* __restrict__ out, const doubl
                    long long total4, int x, int y, int x2, int y2, int x_pre, int y_pre, int clip_in_place,
                    const SelState* __restrict__ st, const float* __restrict__ lut, int lut_kernel_enqueued) {
     if (lut_kernel_enqueued && st->done) return;             // rescale_lut_kernel has written the output
-    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i4 >= total4) return;
+    for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (long long)gridDim.x * blockDim.x) {
     const double vl = vlvh[0], vh = vlvh[1];
     const float fl = (float)vl, fh = (float)vh;     // what `image[image < vl] = vl` stores
     const double den = vh - vl;
@@ -390,6 +389,7 @@ rescale_pad_kernel(float* __restrict__ vol, float* __restrict__ out, const doubl
         if (clip_in_place && vec && changed) *reinterpret_cast<float4*>(row + sx0) = make_float4(vin[0], vin[1], vin[2], vin[3]);
     }
     reinterpret_cast<float4*>(out)[i4] = make_float4(r[0], r[1], r[2], r[3]);
+    }
 }
 
 int preproc_alloc(PreprocWorkspace& ws) {
@@ -455,7 +455,9 @@ int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int 
         rescale_lut_kernel<<<grid, block, 0, st>>>(vol, out, state, ws.lut, x, y, x2, y2, x_pre, y_pre, clip_in_place);
         if (launches) *launches += 1;
     }
-    rescale_pad_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(vol, out, ws.vlvh, total4, x, y, x2, y2,
+    // grid-stride with a bounded grid: when the table-lookup kernel has done the work this launch is 2368 blocks that return at once
+    const long long pad_blocks = (total4 + 255) / 256, pad_cap = (long long)sms * 16;
+    rescale_pad_kernel<<<(unsigned)(pad_blocks < pad_cap ? pad_blocks : pad_cap), 256, 0, st>>>(vol, out, ws.vlvh, total4, x, y, x2, y2,
                                                                           x_pre, y_pre, clip_in_place, state, ws.lut, vec_rows);
     if (launches) *launches += 10;
     UKBB_CUDA(cudaGetLastError());
