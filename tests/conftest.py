@@ -14,6 +14,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """libukbb_fcn.so is a build artefact (git-ignored): build it in-tree when it is missing or older than its sources, exactly
+    as `__graft_entry__.build()` does (nvcc cross-compiles sm_100a without a GPU).  The package has no fallback without it."""
+    from ukbb_cardiac_b200 import build as b
+    if b.needs_build():
+        b.build_library()
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch
