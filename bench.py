@@ -162,7 +162,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on STDOUT when the first communicator is created; the contract is ONE JSON line there
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     S = args.subjects if args.subjects else (2 if args.mode == "fp32" else 256)
     X, Y, Z, T = SA
     nvox = X * Y * Z * T
