@@ -58,6 +58,14 @@ extern "C" {
 #define UKBB_MODE_BF16  2   /* BF16 operands, FP32 accumulate on tcgen05 tensor cores */
 #define UKBB_MODE_FP16  3   /* FP16 operands, FP32 accumulate: same kernels and tensor-core rate as
                                BF16, 11-bit significand (activations are post-BN/ReLU, O(1..100)) */
+/* Split-operand tensor-core modes (the "3x" scheme, cf. 3xTF32): every activation and every weight is carried as
+ * the sum of TWO 16-bit values, v = hi + lo with hi = rn16(v), lo = rn16(v - hi), and every product is evaluated as
+ * hi.hi + lo.hi + hi.lo in the FP32 accumulator (three tcgen05.mma per K step; the lo.lo term is dropped).
+ * Effective significand: 16 bits (BF16X3) / 22 bits (FP16X3, activations clamped to +-65504).  These are the
+ * tensor-core modes that meet the >= 99.9 % label agreement / Dice >= 0.999 tolerance against the float32 reference
+ * on random-init weights; plain BF16 / FP16 do not. */
+#define UKBB_MODE_BF16X3  4
+#define UKBB_MODE_FP16X3  5
 
 #define UKBB_N_CONV 21      /* 13 encoder 3x3 + 5 same_dim 1x1 + fc0 + fc1 + logits */
 #define UKBB_MAX_CLASS 8
@@ -126,11 +134,18 @@ int ukbb_fcn_join(ukbb_fcn* h, void* stream);
 /* Block the host until all work of this handle's device has finished. */
 int ukbb_fcn_sync(ukbb_fcn* h);
 
-/* Test hook (BF16 mode): run conv layer `layer` (1..19, graph order) alone on a device BF16 NHWC
- * tensor in [n][hi][wi][cin] -> out [n][ho][wo][cout] (rows = Y, columns = X), synchronously.
+/* Test hook (tensor-core modes): run conv layer `layer` (graph order: 1..19 in the BF16 / FP16 modes, the 3x3 layers
+ * 1..12 in the x3 modes) alone on a device 16-bit NHWC tensor in [n][hi][wi][cin] -> out [n][ho][wo][cout] (rows = Y,
+ * columns = X), synchronously.  In the x3 modes both tensors have two planes: [2][n][..] = hi plane | lo plane.
  * level_out selects the tile shape used for resolution level 0..4. */
 int ukbb_fcn_debug_conv(ukbb_fcn* h, int layer, const void* in_bf16, int n, int hi, int wi, int level_out,
                         void* out_bf16, void* stream);
+
+/* Test hook (tensor-core modes): copy the first n_elems elements of an intermediate tensor of the most recent
+ * ukbb_fcn_forward out as float32 (hi + lo in the x3 modes).  which: 0 / 1 = encoder ping / pong buffer of resolution
+ * `level` ([n][h>>level][w>>level][16 << level]; level outputs are pong, ping, ping, ping, ping for levels 0..4),
+ * 2 = t_level = fc0 column block applied to same_dim_level ([n][h>>level][w>>level][64], level 1..4). */
+int ukbb_fcn_debug_read(ukbb_fcn* h, int which, int level, float* out_f32, long long n_elems, void* stream);
 
 /* Kernel timer used by bench.py for the roofline line: when enabled, every launch of the fused head kernel
  * (the dominant kernel of the forward) is bracketed by CUDA events on the launching stream.

@@ -1,0 +1,260 @@
+"""GPU parity tests of the tensor-core modes (tcgen05 kernels) through the C ABI.
+
+Tolerance of record (BASELINE.json north_star): >= 99.9 % per-pixel label agreement with the
+float32 reference restatement and Dice >= 0.999 per class (image_utils.py:171-175) on random-init
+weights.  The split-operand modes ("fp16x3", the default, and "bf16x3") are asserted at exactly
+those floors.  The plain 16-bit modes ("bf16", "fp16") are kept as faster opt-in modes that do NOT
+meet the tolerance on a random-init network (experiments/layer_budget.py reproduces their figures
+with plain torch ops); their tests are regression guards at the measured level and say so.
+
+Per-layer unit tests compare every stand-alone conv kernel with the float64 oracle evaluated on
+the SAME rounded inputs and weights, so the only differences are FP32 accumulation order, the
+dropped lo.lo term of the split product and the final rounding.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import deploy_oracle as do
+from oracle import fcn_oracle as fo
+from ukbb_cardiac_b200 import synth
+from ukbb_cardiac_b200 import weights as W
+from ukbb_cardiac_b200.fcn import FCNEngine
+
+from gpu_util import adjudicate_labels, from_device_labels, from_device_logits, to_device_layout
+
+pytestmark = pytest.mark.gpu
+
+TDT = {"bf16": torch.bfloat16, "fp16": torch.float16, "bf16x3": torch.bfloat16, "fp16x3": torch.float16}
+SPLIT = {"bf16": False, "fp16": False, "bf16x3": True, "fp16x3": True}
+X3 = ["fp16x3", "bf16x3"]
+ALL_TC = ["fp16x3", "bf16x3", "fp16", "bf16"]
+# north_star tolerance for the compliant modes; measured regression floors for the plain 16-bit modes
+AGREE_FLOOR = {"fp16x3": 0.999, "bf16x3": 0.999, "fp16": 0.995, "bf16": 0.97}
+DICE_FLOOR = {"fp16x3": 0.999, "bf16x3": 0.999, "fp16": 0.99, "bf16": 0.95}
+# max |logit - float64 logit| / max |logit|
+LOGIT_RTOL = {"fp16x3": 1e-4, "bf16x3": 5e-4, "fp16": 8e-3, "bf16": 5e-2}
+
+
+def round16(a: np.ndarray, dt) -> np.ndarray:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dt).to(torch.float32).numpy()
+
+
+def split16(a: np.ndarray, dt):
+    """v -> (hi, lo) with hi = rn16(v), lo = rn16(v - hi), as float32 arrays."""
+    hi = round16(a, dt)
+    lo = round16(np.asarray(a, dtype=np.float32) - hi, dt)
+    return hi, lo
+
+
+def layer_reference(w, li, x_dev_layout: np.ndarray, dt, split: bool) -> np.ndarray:
+    """float64 conv + BN + ReLU of layer li on a device-layout [N, Y, X, C] input (already representable)."""
+    sp = W.layer_table(4)[li]
+    x_tf = np.transpose(x_dev_layout, (0, 2, 1, 3)).astype(np.float64)             # [N, X, Y, C]
+    k32 = w[W.conv_name(li) + "/kernel"]
+    if split:
+        hi, lo = split16(k32, dt)
+        k = hi.astype(np.float64) + lo.astype(np.float64)
+    else:
+        k = round16(k32, dt).astype(np.float64)
+    y = fo.conv2d_same(torch.from_numpy(np.transpose(x_tf, (0, 3, 1, 2))), k, sp.stride)
+    bn = W.bn_name(li)
+    g, b, m, v = (w[bn + "/" + s].astype(np.float64) for s in ("gamma", "beta", "moving_mean", "moving_variance"))
+    sc = g / np.sqrt(v + 1e-3)
+    y = torch.relu(y * torch.from_numpy(sc).view(1, -1, 1, 1) + torch.from_numpy(b - m * sc).view(1, -1, 1, 1))
+    return np.transpose(y.numpy(), (0, 3, 2, 1))                                    # -> [N, Y, X, C]
+
+
+LAYER_LEVEL = [0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 0, 1, 2, 3, 4, 0, 0]
+
+
+@pytest.fixture(scope="module", params=ALL_TC)
+def engine(request):
+    w = synth.make_weights(0, 4)
+    eng = FCNEngine(w, mode=request.param)
+    yield eng, w, request.param
+    eng.close()
+
+
+@pytest.mark.parametrize("li", list(range(1, 20)))
+def test_tc_layer(engine, li):
+    eng, w, mode = engine
+    dt, split = TDT[mode], SPLIT[mode]
+    if split and li > 12:
+        pytest.skip("the 1x1 layers have no stand-alone kernel in the x3 modes (fused in side_tc / head_ts)")
+    sp = W.layer_table(4)[li]
+    lvl = LAYER_LEVEL[li]
+    lvl_in = lvl - 1 if sp.stride == 2 else lvl
+    n, H, Wd = 3, 32 >> lvl_in, 48 >> lvl_in
+    rng = np.random.default_rng(li)
+    x32 = np.abs(rng.normal(0.0, 1.0, size=(n, H, Wd, sp.cin))).astype(np.float32) if split else rng.normal(0.0, 1.0, size=(n, H, Wd, sp.cin))
+    if split:
+        hi, lo = split16(x32, dt)
+        x = hi.astype(np.float64) + lo.astype(np.float64)
+        xin = torch.from_numpy(np.stack([hi, lo])).to(dt).cuda()
+        o = eng.debug_conv(li, xin, lvl).float().cpu().numpy().astype(np.float64)
+        out = o[0] + o[1]
+    else:
+        x = round16(x32, dt)
+        out = eng.debug_conv(li, torch.from_numpy(x).to(dt).cuda(), lvl).float().cpu().numpy()
+    ref = layer_reference(w, li, x, dt, split)
+    assert out.shape == ref.shape
+    err = np.abs(out - ref)
+    rel, ab = {"bf16": (2.0 ** -7, 2e-3), "fp16": (2.0 ** -10, 3e-4), "bf16x3": (2.0 ** -14, 3e-5), "fp16x3": (2.0 ** -17, 1e-5)}[mode]   # x3: FP32 accumulation over K <= 2304 terms
+    tol = rel * np.abs(ref) + ab * max(1.0, float(np.abs(ref).max()))
+    assert (err <= tol).all(), "layer %d (%s): max err %g at %s, ref there %g; frac bad %g" % (
+        li, sp.role, err.max(), np.unravel_index(err.argmax(), err.shape), ref.flat[err.argmax()], (err > tol).mean())
+
+
+def _check_vs_oracle(mode, img, w, labels, logits):
+    ref = fo.build_fcn(img, w, torch.float64)
+    lg = from_device_logits(logits)
+    rel = np.abs(lg - ref).max() / np.abs(ref).max()
+    assert rel < LOGIT_RTOL[mode], "%s logits rel err %g" % (mode, rel)
+    lab = from_device_labels(labels)
+    if SPLIT[mode]:
+        # every label that differs from the float64 argmax must be a near-tie at the logit tolerance
+        adjudicate_labels(lab, ref, 2 * LOGIT_RTOL[mode] * float(np.abs(ref).max()))
+    agree = (lab == np.argmax(ref, -1)).mean()
+    assert agree >= AGREE_FLOOR[mode], (mode, agree)
+    return rel, agree
+
+
+@pytest.mark.parametrize("mode", ALL_TC)
+@pytest.mark.parametrize("n_class", [4, 2, 3, 6])
+def test_forward_tc_small(n_class, mode):
+    w = synth.make_weights(0, n_class)
+    img = np.random.default_rng(n_class).random((3, 64, 48, 1)).astype(np.float32)
+    with FCNEngine(w, mode=mode) as eng:
+        labels, logits, _ = eng.forward(to_device_layout(img), want_logits=True)
+        torch.cuda.synchronize()
+    _check_vs_oracle(mode, img, w, labels, logits)
+
+
+@pytest.mark.parametrize("mode", X3)
+@pytest.mark.parametrize("shape", [(5, 48, 80), (2, 192, 208), (130, 32, 48), (7, 176, 224), (501, 16, 32)])
+def test_forward_x3_shapes(mode, shape):
+    """Border tiles, partial last tiles of every kernel (13- / 14- / 16-row tiles, 16x16 halo tiles, 128-pixel side tiles), the odd
+    tile counts of the two-CTA clusters, and two sub-batches (501 slices)."""
+    w = synth.make_weights(0, 4)
+    img = np.random.default_rng(shape[0]).random(shape + (1,)).astype(np.float32)
+    with FCNEngine(w, mode=mode) as eng:
+        labels, logits, _ = eng.forward(to_device_layout(img), want_logits=True)
+        torch.cuda.synchronize()
+    _check_vs_oracle(mode, img, w, labels, logits)
+
+
+@pytest.mark.parametrize("mode", ALL_TC)
+def test_intermediate_tensors(mode):
+    """Every materialised intermediate tensor of one forward against the float64 oracle features (localises a wrong kernel)."""
+    w = synth.make_weights(0, 4)
+    n, X, Y = 3, 64, 96
+    img = np.random.default_rng(5).random((n, X, Y, 1)).astype(np.float32)
+    _, feats = fo.build_fcn(img, w, torch.float64, return_features=True)
+    # (which, level) -> oracle feature name: level outputs are b0, b1, a2, a3, a4; the block before the last is the other buffer
+    tensors = {(1, 0): "enc0_1", (0, 1): "enc1_0", (1, 1): "enc1_1", (1, 2): "enc2_1", (0, 2): "enc2_2", (1, 3): "enc3_1", (0, 3): "enc3_2",
+               (1, 4): "enc4_1", (0, 4): "enc4_2"}
+    rtol = {"bf16": 0.05, "fp16": 8e-3, "bf16x3": 3e-4, "fp16x3": 1e-4}[mode]     # up to 12 layers deep
+    with FCNEngine(w, mode=mode) as eng:
+        eng.forward(to_device_layout(img))
+        torch.cuda.synchronize()
+        for (which, level), name in tensors.items():
+            ref = np.transpose(feats[name], (0, 2, 1, 3))                           # [N, X, Y, C] -> device [N, Y, X, C]
+            got = eng.debug_read(which, level, ref.shape).cpu().numpy()
+            rel = np.abs(got - ref).max() / np.abs(ref).max()
+            assert rel < rtol, "%s: %s (buffer %d of level %d) rel err %g" % (mode, name, which, level, rel)
+        # t_l = W_l . same_dim_l with the fc0 BN scale folded in (head_common.cuh)
+        bn = W.bn_name(18)
+        sc = w[bn + "/gamma"].astype(np.float64) / np.sqrt(w[bn + "/moving_variance"].astype(np.float64) + 1e-3)
+        k0 = w[W.conv_name(18) + "/kernel"][0, 0].astype(np.float64) * sc[None, :]  # [160, 64]
+        for l in range(1, 5):
+            s_l = np.transpose(feats["same%d" % l], (0, 2, 1, 3)).astype(np.float64)
+            ref = s_l @ k0[32 * l:32 * l + 32]
+            got = eng.debug_read(2, l, ref.shape).cpu().numpy()
+            rel = np.abs(got - ref).max() / np.abs(ref).max()
+            assert rel < rtol, "%s: t_%d rel err %g" % (mode, l, rel)
+
+
+def _agreement(lab, pred, n_class):
+    return float((lab == pred).mean()), [fo.categorical_dice(lab, pred, k) for k in range(n_class)]
+
+
+@pytest.mark.parametrize("mode", ALL_TC)
+def test_forward_tc_sa_random_init(mode):
+    """Synthetic SA frames through the RANDOM-INIT network against the float32 reference restatement
+    (train_network.py:198-199): the north_star floors for the x3 modes, regression floors for the plain modes."""
+    w = synth.make_weights(0, 4)
+    vol = synth.make_stack(0)
+    img = do.rescale_intensity(vol.copy(order="F"), (1, 99))
+    fr = np.concatenate([np.transpose(img[:, :, :, t], (2, 0, 1)) for t in (0, 20)]).astype(np.float32)[..., None]
+    with FCNEngine(w, mode=mode) as eng:
+        labels, _, _ = eng.forward(to_device_layout(fr))
+        torch.cuda.synchronize()
+    _, pred = fo.session_run(fr, w)
+    agree, dice = _agreement(from_device_labels(labels), pred, 4)
+    print("%s agreement %.5f dice %s" % (mode, agree, dice))
+    assert agree >= AGREE_FLOOR[mode], agree
+    assert min(dice) >= DICE_FLOOR[mode], dice
+
+
+def test_full_subject_c1_default_mode():
+    """BASELINE config C1: one whole synthetic SA subject (192 x 208 x 10 x 50 = 500 slices) through the host-buffer call in the
+    DEFAULT mode against the reference loop restated (deploy_network.py:89-116, one sess.run per frame), at the north_star
+    floors; thresholds, ES frame and class counts included."""
+    w = synth.make_weights(0, 4)
+    vol = synth.make_stack(3)
+    pred_ref, _ = do.deploy_sequence(vol.copy(order="F"), do.make_runner(w))
+    with FCNEngine(w) as eng:
+        assert eng.mode == "fp16x3"
+        lab, (vl, vh), counts = eng.segment_volume(vol)
+    assert vl == do.percentile_linear(vol, 1) and vh == do.percentile_linear(vol, 99)
+    agree, dice = _agreement(lab, pred_ref, 4)
+    print("C1 full subject: agreement %.6f dice %s" % (agree, dice))
+    assert agree >= 0.999 and min(dice) >= 0.999, (agree, dice)
+    assert counts.sum() == lab.size
+    for k in range(4):
+        assert counts[:, :, k].sum() == (lab == k).sum()
+    # ES frame rule of deploy_network.py:125-131 (argmin of the LV cavity) from the device counts == from the oracle labels
+    es_dev = int(np.argmin(counts[:, :, 1].sum(axis=1)))
+    es_ref = int(np.argmin([(pred_ref[..., t] == 1).sum() for t in range(pred_ref.shape[3])]))
+    assert es_dev == es_ref
+
+
+@pytest.mark.parametrize("n_class", [2, 3])
+def test_full_sequence_c2_default_mode(n_class):
+    """BASELINE config C2: full-size long-axis sequences (210 x 171 x 1 x 50 -> padded 224 x 176, pad 7/7 and 2/3), la_2ch
+    (2 classes) and la_4ch (3 classes), default mode, north_star floors."""
+    w = synth.make_weights(0, n_class)
+    vol = synth.make_stack(7 + n_class, (210, 171, 1, 50))
+    pred_ref, _ = do.deploy_sequence(vol.copy(order="F"), do.make_runner(w))
+    with FCNEngine(w) as eng:
+        lab, (vl, vh), counts = eng.segment_volume(vol)
+    assert vl == do.percentile_linear(vol, 1) and vh == do.percentile_linear(vol, 99)
+    agree, dice = _agreement(lab, pred_ref, n_class)
+    print("C2 %d classes: agreement %.6f dice %s" % (n_class, agree, dice))
+    assert agree >= 0.999 and min(dice) >= 0.999, (agree, dice)
+    assert counts.sum() == lab.size
+
+
+@pytest.mark.parametrize("mode", ALL_TC)
+def test_segment_volume_tc_la(mode):
+    w = synth.make_weights(0, 2)
+    vol = synth.make_stack(5, (50, 43, 1, 6))
+    pred_ref, _ = do.deploy_sequence(vol.copy(order="F"), do.make_runner(w))
+    with FCNEngine(w, mode=mode) as eng:
+        lab, (vl, vh), counts = eng.segment_volume(vol)
+    assert vl == do.percentile_linear(vol, 1) and vh == do.percentile_linear(vol, 99)
+    assert (lab == pred_ref).mean() >= AGREE_FLOOR[mode]
+    assert counts.sum() == lab.size
+
+
+@pytest.mark.parametrize("mode", ["fp16x3", "bf16"])
+def test_forward_is_deterministic(mode):
+    w = synth.make_weights(0, 4)
+    img = np.random.default_rng(1).random((9, 64, 96, 1)).astype(np.float32)
+    dev = to_device_layout(img)
+    with FCNEngine(w, mode=mode) as eng:
+        l1, g1, _ = eng.forward(dev, want_logits=True)
+        l2, g2, _ = eng.forward(dev, want_logits=True)
+        torch.cuda.synchronize()
+    assert torch.equal(g1, g2) and torch.equal(l1, l2)

@@ -17,6 +17,8 @@ LIB_PATH = os.path.join(HERE, "libukbb_fcn.so")
 MODE_FP32 = 0
 MODE_BF16 = 2
 MODE_FP16 = 3
+MODE_BF16X3 = 4     # split operands (hi + lo 16-bit pairs, three tcgen05.mma per K step): 16-bit significand
+MODE_FP16X3 = 5     # same with FP16 pieces: 22-bit significand -- the default tensor-core mode
 N_CONV = 21
 MAX_CLASS = 8
 
@@ -49,6 +51,7 @@ SIGNATURES = {
     "ukbb_fcn_sync": (C.c_int, [C.c_void_p]),
     "ukbb_fcn_debug_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p]),
+    "ukbb_fcn_debug_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
     "ukbb_fcn_kernel_timer": (C.c_int, [C.c_void_p, C.c_int]),
     "ukbb_fcn_kernel_timer_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ukbb_fcn_launch_count": (C.c_longlong, [C.c_void_p]),

@@ -90,7 +90,7 @@ static int ensure_ws(Engine* h, int nb, int hh, int ww) {
     if (h->ws.nb >= nb && h->ws.h == hh && h->ws.w == ww) return UKBB_OK;
     UKBB_CUDA(cudaDeviceSynchronize());
     free_ws(h);
-    const size_t esz = h->mode == UKBB_MODE_FP32 ? 4 : 2;
+    const size_t esz = 4;                                 // FP32 mode only (the tensor-core modes own their workspace: tc_forward.cu)
     for (int l = 0; l < 5; ++l) {
         const size_t px = (size_t)nb * (hh >> l) * (ww >> l);
         UKBB_CUDA(cudaMalloc(&h->ws.a[l], px * kNFilter[l] * esz));
@@ -98,11 +98,9 @@ static int ensure_ws(Engine* h, int nb, int hh, int ww) {
         UKBB_CUDA(cudaMalloc(&h->ws.s[l], px * 32 * esz));
     }
     const size_t px = (size_t)nb * hh * ww;
-    if (h->mode == UKBB_MODE_FP32) {
-        UKBB_CUDA(cudaMalloc(&h->ws.cat, px * 160 * esz));
-        UKBB_CUDA(cudaMalloc(&h->ws.f0, px * 64 * esz));
-        UKBB_CUDA(cudaMalloc(&h->ws.f1, px * 64 * esz));
-    }
+    UKBB_CUDA(cudaMalloc(&h->ws.cat, px * 160 * esz));
+    UKBB_CUDA(cudaMalloc(&h->ws.f0, px * 64 * esz));
+    UKBB_CUDA(cudaMalloc(&h->ws.f1, px * 64 * esz));
     h->ws.nb = nb; h->ws.h = hh; h->ws.w = ww;
     return UKBB_OK;
 }
@@ -180,7 +178,7 @@ static int forward_any(Engine* h, const float* image, int n, int x2, int y2, int
     h->counts_n = n;
     if (h->mode == UKBB_MODE_FP32)
         return forward_fp32(h, image, n, x2, y2, x_pre, y_pre, x, y, labels, logits, prob, h->d_counts, st);
-    return forward_bf16(h, image, n, x2, y2, x_pre, y_pre, x, y, labels, logits, prob, h->d_counts, st);
+    return forward_tc(h, image, n, x2, y2, x_pre, y_pre, x, y, labels, logits, prob, h->d_counts, st);
 }
 
 }  // namespace ukbb
@@ -197,7 +195,8 @@ int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode
     *out = nullptr;
     UKBB_REQUIRE(w->n_conv == UKBB_N_CONV && w->conv, "create: expected %d conv layers, got %d", UKBB_N_CONV, w->n_conv);
     UKBB_REQUIRE(n_class >= 2 && n_class <= UKBB_MAX_CLASS, "create: n_class=%d not in [2,%d]", n_class, UKBB_MAX_CLASS);
-    UKBB_REQUIRE(mode == UKBB_MODE_FP32 || mode == UKBB_MODE_BF16 || mode == UKBB_MODE_FP16, "create: unknown mode %d", mode);
+    UKBB_REQUIRE(mode == UKBB_MODE_FP32 || mode == UKBB_MODE_BF16 || mode == UKBB_MODE_FP16 || mode == UKBB_MODE_BF16X3 || mode == UKBB_MODE_FP16X3,
+                 "create: unknown mode %d", mode);
     for (int i = 0; i < UKBB_N_CONV; ++i) {
         int ks, cin, cout, stride;
         expected_layer(i, n_class, &ks, &cin, &cout, &stride);
@@ -226,7 +225,7 @@ int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode
     int rc = UKBB_OK;
     for (int i = 0; i < UKBB_N_CONV && !rc; ++i) rc = upload_layer(h->layers[i], w->conv[i], w->bn_eps, i == UKBB_N_CONV - 1);
     if (!rc) rc = preproc_alloc(h->pre);
-    if (!rc && mode != UKBB_MODE_FP32) rc = bf16_prepare(h, w);
+    if (!rc && mode != UKBB_MODE_FP32) rc = tc_prepare(h, w);
     if (!rc) {
         cudaError_t e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
@@ -251,9 +250,8 @@ void ukbb_fcn_destroy(ukbb_fcn* hh) {
     cudaDeviceSynchronize();
     for (int i = 0; i < UKBB_N_CONV; ++i) {
         cudaFree(h->layers[i].w_f32); cudaFree(h->layers[i].scale); cudaFree(h->layers[i].shift);
-        cudaFree(h->layers[i].w_bf16);
     }
-    bf16_release(h);
+    tc_release(h);
     free_ws(h);
     preproc_free(h->pre);
     cudaFree(h->d_counts);
@@ -291,6 +289,7 @@ int ukbb_fcn_class_counts(ukbb_fcn* hh, long long* counts, int n, void* stream) 
     Engine* h = reinterpret_cast<Engine*>(hh);
     UKBB_REQUIRE(h && counts, "class_counts: null argument");
     UKBB_REQUIRE(n > 0 && n <= h->counts_n, "class_counts: n=%d but the last forward had %d slices", n, h->counts_n);
+    UKBB_CUDA(cudaSetDevice(h->device));
     UKBB_CUDA(cudaMemcpyAsync(counts, h->d_counts, (size_t)n * h->n_class * sizeof(long long), cudaMemcpyDeviceToDevice,
                               (cudaStream_t)stream));
     return UKBB_OK;
@@ -359,6 +358,7 @@ int ukbb_fcn_segment_host(ukbb_fcn* hh, const float* vol, int x, int y, int z, i
 int ukbb_fcn_join(ukbb_fcn* hh, void* stream) {
     Engine* h = reinterpret_cast<Engine*>(hh);
     UKBB_REQUIRE(h, "join: null handle");
+    UKBB_CUDA(cudaSetDevice(h->device));
     for (int s = 0; s < 2; ++s) UKBB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_d2h[s], 0));
     return UKBB_OK;
 }
@@ -377,7 +377,15 @@ int ukbb_fcn_debug_conv(ukbb_fcn* hh, int layer, const void* in_bf16, int n, int
     UKBB_REQUIRE(h && in_bf16 && out_bf16, "debug_conv: null argument");
     UKBB_REQUIRE(h->mode != UKBB_MODE_FP32, "debug_conv: engine is not in a tensor-core mode");
     UKBB_CUDA(cudaSetDevice(h->device));
-    return debug_conv_bf16(h, layer, in_bf16, n, hi, wi, level_out, out_bf16, (cudaStream_t)stream);
+    return debug_conv_tc(h, layer, in_bf16, n, hi, wi, level_out, out_bf16, (cudaStream_t)stream);
+}
+
+int ukbb_fcn_debug_read(ukbb_fcn* hh, int which, int level, float* out_f32, long long n_elems, void* stream) {
+    Engine* h = reinterpret_cast<Engine*>(hh);
+    UKBB_REQUIRE(h && out_f32, "debug_read: null argument");
+    UKBB_REQUIRE(h->mode != UKBB_MODE_FP32, "debug_read: engine is not in a tensor-core mode");
+    UKBB_CUDA(cudaSetDevice(h->device));
+    return debug_read_tc(h, which, level, out_f32, n_elems, (cudaStream_t)stream);
 }
 
 int ukbb_fcn_kernel_timer(ukbb_fcn* hh, int enable) {

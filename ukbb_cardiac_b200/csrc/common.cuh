@@ -37,7 +37,6 @@ struct ConvLayer {
     float* w_f32 = nullptr;       // [ks*ks][cin][cout]
     float* scale = nullptr;       // [cout]  gamma * rsqrt(var + eps)   (1 for logits)
     float* shift = nullptr;       // [cout]  beta - mean * scale        (bias for logits)
-    __nv_bfloat16* w_bf16 = nullptr;  // tensor-core layout, see conv_tc.cu
     int relu;
 };
 

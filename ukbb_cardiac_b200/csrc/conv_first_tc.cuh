@@ -22,26 +22,52 @@
 //                 8 STS.128; groups outside the image are written as ZEROS: SAME padding of conv0_1 pads a0, not the image].
 //                 (Separate builder / finisher warps, 22 warps at 80 registers, spilled and measured slower: 343 vs 266 us.)
 // TMEM columns: conv0_1 accumulators 2 x 64 | D0 2 stages x 2 blocks x 64 | A0 2 stages x 2 blocks x 32 = 512.
+//
+// SPLIT (x3 modes): the a0 patch is written as a hi and a lo patch (a0 = hi + lo), conv0_1 runs three UMMAs per K-slice against the
+// hi and lo weight sets, and b0 leaves as two planes through direct 256-bit stores (as conv_group.cuh).  conv0_0 itself is unchanged:
+// its hi/lo split of the FP32 image and weights is what the x3 modes do everywhere else.
 #pragma once
 #include "tc_common.cuh"
 #include "conv_group.cuh"
-#include "conv_first.cuh"      // ConvFirstParams, tma_load_3d
-#include "head_ts.cuh"         // umma_ts_lohi, tmem_st32, add_relu_pack
+#include "head_common.cuh"     // add_relu_pack / add_relu_split
 
 namespace ukbb {
 
+struct ConvFirstParams {
+    int tiles_x, tiles_y, n_tiles;
+    int h, w4;                      // image rows; image columns / 4 (pixel groups per row)
+    const float* scale;             // conv0_1 folded BN [16]
+    const float* shift;
+    float shift0[16];               // conv0_0 folded BN shift (the scale is folded into its weights)
+    uint32_t* out;                  // split modes: b0 hi plane [n][h][w4 groups][64 elements] as 32-bit words
+    long long out_lo;               //              offset of the lo plane in 32-bit words
+};
+
+namespace tc {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+}  // namespace tc
+
+template <bool SPLIT = false>
 struct ConvFirstTcCfg {
     static constexpr int PU = 10, PR = 18, J = 6, N = 64;
     static constexpr int GROUPS = PU * PR;                      // 180 patch group rows per tile
     static constexpr int BUILDERS = 6;                          // builder warps with work (8 launched: TMEM lane quarters)
-    static constexpr int PATCH_BYTES = (GROUPS * 128 + 1023) / 1024 * 1024;
-    static constexpr int A_STAGES = 4;
+    static constexpr int PLANE_BYTES = (GROUPS * 128 + 1023) / 1024 * 1024;
+    static constexpr int PATCH_BYTES = (SPLIT ? 2 : 1) * PLANE_BYTES;     // hi patch | lo patch
+    static constexpr int A_STAGES = SPLIT ? 2 : 4;
     static constexpr int B_TILE = 2048;
     static constexpr int NB_TILES = 3 * J;
-    static constexpr int B_BYTES = NB_TILES * B_TILE;
+    static constexpr int B_SET = NB_TILES * B_TILE;
+    static constexpr int B_BYTES = (SPLIT ? 2 : 1) * B_SET;     // hi tiles | lo tiles
     static constexpr int B0_BYTES = 64 * 128;                   // conv0_0 weights [64 rows][64 K] 16-bit, 128 B swizzle
-    static constexpr int OUT_BYTES = 128 * 128;
-    static constexpr int IMG_W = 48, IMG_H = 20;
+    static constexpr int OUT_BYTES = SPLIT ? 0 : 128 * 128;
+    static constexpr int IMG_W = 48, IMG_H = 20;                // FP32 box: columns x0 - 8 .. x0 + 39, rows y0 - 2 .. y0 + 17 (TMA needs the
+                                                                // box origin 16-byte aligned in the inner dimension: experiments/tma_probe_img.cu)
     static constexpr int IMG_TX = IMG_W * IMG_H * 4;
     static constexpr int IMG_BYTES = (IMG_TX + 127) / 128 * 128;
     static constexpr int IMG_STAGES = 4;
@@ -50,15 +76,16 @@ struct ConvFirstTcCfg {
     static constexpr int COL_ACC = 0, COL_D0 = 128, COL_A0 = 384;
     static constexpr int SMEM_BYTES = A_STAGES * PATCH_BYTES + B_BYTES + B0_BYTES + 2 * OUT_BYTES + IMG_STAGES * IMG_BYTES + 256 /*barriers*/ +
                                       2 * N * 4 + 1024 /*align*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <bool F16>
-__global__ void __launch_bounds__(ConvFirstTcCfg::THREADS, 1)
+template <bool F16, bool SPLIT = false>
+__global__ void __launch_bounds__(ConvFirstTcCfg<>::THREADS, 1)
 conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_out,
                      const __grid_constant__ ConvFirstParams p) {
     using namespace tc;
-    using Cfg = ConvFirstTcCfg;
+    using Cfg = ConvFirstTcCfg<SPLIT>;
     constexpr int AST = Cfg::A_STAGES, IST = Cfg::IMG_STAGES, J = Cfg::J, PU = Cfg::PU, N = Cfg::N;
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
@@ -111,8 +138,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
     if (warp == 0) {
         // ===================== TMA producer: weights once, one FP32 image box per tile =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(wfull, Cfg::NB_TILES * Cfg::B_TILE + Cfg::B0_BYTES);
-            for (int t = 0; t < Cfg::NB_TILES; ++t) tma_load_2d(b_base + t * Cfg::B_TILE, &map_b, wfull, 0, t * N);
+            mbar_arrive_expect_tx(wfull, (SPLIT ? 2 : 1) * Cfg::NB_TILES * Cfg::B_TILE + Cfg::B0_BYTES);
+            for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) tma_load_2d(b_base + t * Cfg::B_TILE, &map_b, wfull, 0, t * N);   // hi tiles, then lo tiles
             tma_load_2d(b0_base, &map_b0, wfull, 0, 0);
             griddep_wait();
             TileWalk w;
@@ -153,8 +180,12 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                         const int ro = jj < 0 ? -1 : jj / 4;
                         const int sub = jj - ro * 4;
                         const int arow = ky * PU + 1 + ro;
-                        umma_bf16_lohi(d, a_lo + ((arow * 128 + sub * 32) >> 4), a_hi, b_lo + (((ky * J + j) * Cfg::B_TILE) >> 4), b_hi, idesc,
-                                       (ky | j) != 0 ? 1u : 0u);
+                        const uint32_t ao = (uint32_t)((arow * 128 + sub * 32) >> 4), bo = (uint32_t)(((ky * J + j) * Cfg::B_TILE) >> 4);
+                        umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (ky | j) != 0 ? 1u : 0u);
+                        if (SPLIT) {
+                            umma_bf16_lohi(d, a_lo + (Cfg::PLANE_BYTES >> 4) + ao, a_hi, b_lo + bo, b_hi, idesc, 1u);                // lo . hi
+                            umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + (Cfg::B_SET >> 4) + bo, b_hi, idesc, 1u);                      // hi . lo
+                        }
                     }
                 umma_commit(a_empty(as));
                 umma_commit(tfull(acc));
@@ -245,6 +276,45 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             const int s = i & 1, as = i % AST;
             mbar_wait(BAR(D0_FULL + s), ((uint32_t)i >> 1) & 1u);
             tc_fence_after();
+            // SAME padding of conv0_1 pads a0 with zeros: groups outside the image are zero, not conv0_0 of a zero image
+            const int y = w.ty * 16 - 1 + py, gx = w.tx * 8 - 1 + pg;
+            const bool inside = y >= 0 && y < p.h && gx >= 0 && gx < p.w4;
+            if (SPLIT) {
+                // 16 accumulator columns (one pixel) at a time: hi and lo rows of the patch, two swizzled STS.128 each
+                mbar_wait(a_empty(as), ((uint32_t)(i / AST) & 1u) ^ 1u);
+                const uint32_t row = smem_base + as * Cfg::PATCH_BYTES + (uint32_t)g * 128u;
+#pragma unroll
+                for (int qt = 0; qt < 4; ++qt) {
+                    uint32_t d[16], oh[8], ol[8];
+                    tmem_ld16(lane_base + Cfg::COL_D0 + (s * 2 + m) * 64 + 16 * qt, d);
+                    tmem_ld_wait();
+                    if (qt == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(D0_EMPTY + s));
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        add_relu_split<F16>(d[2 * c], d[2 * c + 1], p.shift0[2 * c], p.shift0[2 * c + 1], oh[c], ol[c]);
+                        if (!inside) { oh[c] = 0u; ol[c] = 0u; }
+                    }
+                    if (active) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const uint32_t dst = row + (((uint32_t)(2 * qt + c) ^ ((uint32_t)g & 7u)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(oh[4 * c]), "r"(oh[4 * c + 1]), "r"(oh[4 * c + 2]),
+                                         "r"(oh[4 * c + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + Cfg::PLANE_BYTES), "r"(ol[4 * c]), "r"(ol[4 * c + 1]),
+                                         "r"(ol[4 * c + 2]), "r"(ol[4 * c + 3]) : "memory");
+                        }
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full(as));
+                w.next();
+                continue;
+            }
             uint32_t o[32];
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -258,9 +328,6 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(D0_EMPTY + s));
-            // SAME padding of conv0_1 pads a0 with zeros: groups outside the image are zero, not conv0_0 of a zero image
-            const int y = w.ty * 16 - 1 + py, gx = w.tx * 8 - 1 + pg;
-            const bool inside = y >= 0 && y < p.h && gx >= 0 && gx < p.w4;
             mbar_wait(a_empty(as), ((uint32_t)(i / AST) & 1u) ^ 1u);
             if (active) {
                 const uint32_t row = smem_base + as * Cfg::PATCH_BYTES + (uint32_t)g * 128u;
@@ -298,6 +365,26 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            if (SPLIT) {
+                const int y = w.ty * 16 + (r >> 3), gx = w.tx * 8 + (r & 7);
+                const bool live = y < p.h && gx < p.w4;
+                uint32_t* dst = p.out + (((size_t)w.n * p.h + y) * p.w4 + gx) * 32;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t oh[8], ol[8];
+#pragma unroll
+                    for (int c = 0; c < 16; c += 4) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
+                        bn_relu_split<F16>(v[16 * c8 + c], v[16 * c8 + c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
+                        bn_relu_split<F16>(v[16 * c8 + c + 2], v[16 * c8 + c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1],
+                                           ol[c / 2 + 1]);
+                    }
+                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
+                }
+                w.next();
+                continue;
+            }
             uint32_t o[32];
 #pragma unroll
             for (int c = 0; c < 64; c += 4) {
@@ -323,7 +410,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             }
             w.next();
         }
-        if (issuer) bulk_wait<0>();
+        if (issuer && !SPLIT) bulk_wait<0>();
     }
     tc_fence_before();
     __syncthreads();

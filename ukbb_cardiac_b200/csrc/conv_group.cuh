@@ -31,32 +31,45 @@ struct ConvGroupParams {
     int tiles_x, tiles_y, n_tiles;
     const float* scale;             // [COUT]
     const float* shift;             // [COUT]
+    // split ("x3") mode: hi / lo planes.  Input lo plane = slices [lo_n, ...) of the patch tensor map; the output is written with
+    // direct 256-bit stores (no staging tile: the shared memory holds two patches per stage and both weight sets instead)
+    int lo_n;
+    uint32_t* out;                  // hi plane, [n][ho][wog groups][64 elements]
+    long long out_lo;               // offset of the lo plane in 32-bit words
+    int ho, wog;
 };
 
-template <int CC, int COUT, int STRIDE>
+// SPLIT: operands are hi + lo pairs of 16-bit values and every K-slice is three UMMAs (hi.hi + lo.hi + hi.lo, conv_tc.cu).
+// TROWS: output rows per tile (<= 16; the UMMA still has M = 128 = 16 rows x 8 groups, rows >= TROWS are idle): the 64 -> 64 split
+// instance holds 144 KB of weights and fits two (hi, lo) patch stages only with 14-row tiles.
+template <int CC, int COUT, int STRIDE, bool SPLIT = false>
 struct ConvGroupCfg {
     static constexpr int G = 64 / CC;                          // input pixels per 128-byte row
     static constexpr int GOUT = STRIDE == 1 ? G : G / 2;       // output pixels per UMMA row
     static constexpr int N = GOUT * COUT;
     static constexpr int J = STRIDE == 1 ? G + 2 : G + 1;      // K-slices per kernel row
     static constexpr int KS = CC / 16;
+    static constexpr int TROWS = (SPLIT && CC == 64 && STRIDE == 1) ? 14 : 16;
     static constexpr int PU = STRIDE == 1 ? 10 : 9;            // patch groups per row
-    static constexpr int PR = STRIDE == 1 ? 18 : 33;           // patch rows
+    static constexpr int PR = STRIDE == 1 ? TROWS + 2 : 2 * TROWS + 1;   // patch rows
     static constexpr int PATCH_TX = PR * PU * 128;
     static constexpr int PATCH_BYTES = (PATCH_TX + 1023) / 1024 * 1024;
+    static constexpr int A_STAGE_BYTES = (SPLIT ? 2 : 1) * PATCH_BYTES;   // hi patch | lo patch
     static constexpr int B_ROW = CC * 2;
     static constexpr int B_TILE = (N * B_ROW + 1023) / 1024 * 1024;
     static constexpr int NB_TILES = 3 * J;
-    static constexpr int B_BYTES = NB_TILES * B_TILE;
-    static constexpr int OUT_BYTES = 128 * 128;                // staging tile [128 rows][128 B]
-    static constexpr int A_MAX = (200 * 1024 - B_BYTES - 2 * OUT_BYTES) / PATCH_BYTES;
+    static constexpr int B_SET = NB_TILES * B_TILE;
+    static constexpr int B_BYTES = (SPLIT ? 2 : 1) * B_SET;    // hi tiles | lo tiles
+    static constexpr int OUT_BYTES = SPLIT ? 0 : 128 * 128;    // staging tile [128 rows][128 B]
+    static constexpr int A_MAX = ((SPLIT ? 224 : 200) * 1024 - B_BYTES - 2 * OUT_BYTES) / A_STAGE_BYTES;
     static constexpr int A_STAGES = A_MAX > 4 ? 4 : A_MAX;
     static constexpr int ACC_STAGES = 2;
     static constexpr int TMEM_COLS = 128;
-    static constexpr int SMEM_BYTES = A_STAGES * PATCH_BYTES + B_BYTES + 2 * OUT_BYTES + 1024 + 256 + 2 * N * 4;
+    static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_BYTES + 2 * OUT_BYTES + 1024 + 256 + 2 * N * 4;
     static_assert(N == 64, "pixel-group kernel is built for N = Gout * Cout = 64");
     static_assert(STRIDE == 1 || G >= 2, "stride 2 needs at least two pixels per row");
     static_assert(A_STAGES >= 2, "need at least two patch stages");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 namespace tc {
@@ -86,6 +99,24 @@ __device__ __forceinline__ uint32_t bn_relu_pack(uint32_t a0, uint32_t a1, float
     else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// same arithmetic, but the result is split into 16-bit hi and lo pieces (x3 modes): v = max(a * sc + sh, 0) ~ hi + lo
+template <bool F16>
+__device__ __forceinline__ void bn_relu_split(uint32_t a0, uint32_t a1, float2 sc, float2 sh, uint32_t& hi, uint32_t& lo) {
+    uint64_t a, b, c, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(sc.x), "f"(sc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(sh.x), "f"(sh.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    float x0, x1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
+    split_pack<F16>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
+}
+// one 256-bit global store (STG.256): a full 32-byte sector per thread
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                  "r"(c1), "r"(c2), "r"(c3)
@@ -114,17 +145,17 @@ struct TileWalk {
     }
 };
 
-template <int CC, int COUT, int STRIDE, bool F16>
+template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT = false>
 __global__ void __launch_bounds__(256, 1)
 conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const ConvGroupParams p) {
     using namespace tc;
-    using Cfg = ConvGroupCfg<CC, COUT, STRIDE>;
-    constexpr int AST = Cfg::A_STAGES, G = Cfg::G, J = Cfg::J, KS = Cfg::KS, PU = Cfg::PU, N = Cfg::N;
+    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT>;
+    constexpr int AST = Cfg::A_STAGES, G = Cfg::G, J = Cfg::J, KS = Cfg::KS, PU = Cfg::PU, N = Cfg::N, TROWS = Cfg::TROWS;
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_base = smem_base + AST * Cfg::PATCH_BYTES;
+    const uint32_t b_base = smem_base + AST * Cfg::A_STAGE_BYTES;
     const uint32_t out_base = b_base + Cfg::B_BYTES;
     const uint32_t bar_base = out_base + 2 * Cfg::OUT_BYTES;
     // barriers: a_full[AST] a_empty[AST] tfull[2] tempty[2] wfull | tmem slot
@@ -161,8 +192,8 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(wfull, Cfg::NB_TILES * N * Cfg::B_ROW);
-            for (int t = 0; t < Cfg::NB_TILES; ++t) tma_load_2d(b_base + t * Cfg::B_TILE, &map_b, wfull, 0, t * N);
+            mbar_arrive_expect_tx(wfull, (SPLIT ? 2 : 1) * Cfg::NB_TILES * N * Cfg::B_ROW);
+            for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) tma_load_2d(b_base + t * Cfg::B_TILE, &map_b, wfull, 0, t * N);   // hi tiles, then lo tiles
             griddep_wait();
             TileWalk w;
             w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
@@ -170,9 +201,11 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t aph = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 mbar_wait(a_empty(as), aph ^ 1);
-                mbar_arrive_expect_tx(a_full(as), Cfg::PATCH_TX);
-                if (STRIDE == 1) tma_load_4d(smem_base + as * Cfg::PATCH_BYTES, &map_a, a_full(as), 0, w.tx * 8 - 1, w.ty * 16 - 1, w.n);
-                else tma_load_4d(smem_base + as * Cfg::PATCH_BYTES, &map_a, a_full(as), 0, w.tx * 8, w.ty * 32, w.n);
+                mbar_arrive_expect_tx(a_full(as), (SPLIT ? 2 : 1) * Cfg::PATCH_TX);
+                const uint32_t dst = smem_base + as * Cfg::A_STAGE_BYTES;
+                const int cx = STRIDE == 1 ? w.tx * 8 - 1 : w.tx * 8, cy = STRIDE == 1 ? w.ty * TROWS - 1 : w.ty * 2 * TROWS;
+                tma_load_4d(dst, &map_a, a_full(as), 0, cx, cy, w.n);
+                if (SPLIT) tma_load_4d(dst + Cfg::PATCH_BYTES, &map_a, a_full(as), 0, cx, cy, p.lo_n + w.n);
                 if (++as == AST) { as = 0; aph ^= 1; }
                 w.next();
             }
@@ -194,7 +227,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_wait(a_full(as), aph);
             tc_fence_after();
             const uint32_t d = tmem_base + acc * N;
-            const uint32_t a_lo = (((smem_base + as * Cfg::PATCH_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t a_lo = (((smem_base + as * Cfg::A_STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
             if (leader) {
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
@@ -206,9 +239,15 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const int sub = jj - ro * G;
                         const int arow = STRIDE == 1 ? ky * PU + 1 + ro : ky * PU + ro;
 #pragma unroll
-                        for (int ks = 0; ks < KS; ++ks)
-                            umma_bf16_lohi(d, a_lo + ((arow * 128 + sub * CC * 2 + ks * 32) >> 4), a_hi,
-                                           b_lo + (((ky * J + j) * Cfg::B_TILE + ks * 32) >> 4), b_hi, idesc, (ky | j | ks) != 0 ? 1u : 0u);
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint32_t ao = (uint32_t)((arow * 128 + sub * CC * 2 + ks * 32) >> 4);
+                            const uint32_t bo = (uint32_t)(((ky * J + j) * Cfg::B_TILE + ks * 32) >> 4);
+                            umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (ky | j | ks) != 0 ? 1u : 0u);
+                            if (SPLIT) {
+                                umma_bf16_lohi(d, a_lo + (Cfg::PATCH_BYTES >> 4) + ao, a_hi, b_lo + bo, b_hi, idesc, 1u);            // lo . hi
+                                umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + (Cfg::B_SET >> 4) + bo, b_hi, idesc, 1u);                  // hi . lo
+                            }
+                        }
                     }
                 umma_commit(a_empty(as));
                 umma_commit(tfull(acc));
@@ -238,6 +277,27 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));         // accumulator is in registers: release it to the MMA warp
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            if (SPLIT) {
+                // hi / lo pieces, 128 contiguous bytes each per thread (this row's group), four 256-bit stores per plane
+                const int row = r >> 3, y = w.ty * TROWS + row, gx = w.tx * 8 + (r & 7);
+                const bool live = row < TROWS && y < p.ho && gx < p.wog;
+                uint32_t* dst = p.out + (((size_t)w.n * p.ho + y) * p.wog + gx) * 32;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t oh[8], ol[8];
+#pragma unroll
+                    for (int c = 0; c < 16; c += 4) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
+                        bn_relu_split<F16>(v[16 * c8 + c], v[16 * c8 + c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
+                        bn_relu_split<F16>(v[16 * c8 + c + 2], v[16 * c8 + c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1],
+                                           ol[c / 2 + 1]);
+                    }
+                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
+                }
+                w.next();
+                continue;
+            }
             uint32_t o[32];
 #pragma unroll
             for (int c = 0; c < 64; c += 4) {
@@ -259,7 +319,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (issuer) bulk_wait_read<0>();                 // store of tile i - 1 has left its staging set
             named_bar_sync(1, 128);
             if (issuer) {
-                tma_store_4d(&map_out, out_base + (i & 1) * Cfg::OUT_BYTES, 0, w.tx * 8, w.ty * 16, w.n);
+                tma_store_4d(&map_out, out_base + (i & 1) * Cfg::OUT_BYTES, 0, w.tx * 8, w.ty * TROWS, w.n);
                 bulk_commit();
             }
             w.next();

@@ -26,15 +26,22 @@ struct ConvHaloParams {
     int tiles_x, tiles_y, n_tiles;
     int ho, wo, n;
     int relu, fp16;
+    int lo_n;                       // split mode: slice index of the lo plane in the input tensor map
+    long long out_lo;               // split mode: element offset of the lo plane of `out`
     const float* scale;
     const float* shift;
     __nv_bfloat16* out;             // [n][ho][wo][COUT]
 };
 
-template <int CC, int COUT, bool RESIDENT, int NKB /* 9 * chunks when RESIDENT */>
+// SPLIT (x3 modes, streamed weights only): a patch stage holds the hi and the lo patch of a chunk, and the weight stream alternates
+// hi / lo tiles: per (chunk, tap) the issuer takes the hi tile (UMMAs A_hi.B_hi and A_lo.B_hi), then the lo tile (A_hi.B_lo).  The
+// split instances use 32-channel chunks (64-byte rows) so that two (hi, lo) patch stages and an 8-deep weight ring still fit.
+template <int CC, int COUT, bool RESIDENT, int NKB /* 9 * chunks when RESIDENT */, bool SPLIT = false>
 struct ConvHaloCfg {
+    static_assert(!SPLIT || !RESIDENT, "the split variant streams its weights");
     static constexpr int RB = CC * 2;                                   // bytes per patch row (pixel)
-    static constexpr int PATCH_BYTES = (324 * RB + 1023) / 1024 * 1024;
+    static constexpr int PLANE_BYTES = (324 * RB + 1023) / 1024 * 1024;
+    static constexpr int PATCH_BYTES = (SPLIT ? 2 : 1) * PLANE_BYTES;
     static constexpr int B_TILE = (COUT * RB + 1023) / 1024 * 1024;
     // streamed weights: the ring must cover the ~2000-cycle latency of an L2 fetch -- with four 16 KB stages (512 cycles of UMMAs
     // each) the tensor pipe waited for weights half of the time (7350 cycles per chunk for 3456 cycles of UMMAs); two patch stages
@@ -59,12 +66,12 @@ struct ConvHaloCfg {
 // multicast that lands at the same shared-memory offset in both CTAs and signals both b_full barriers -- and a ring slot is refilled
 // only after BOTH tensor pipes have consumed it (tcgen05.commit multicast on both b_empty barriers, count 2).  The level-3/4 layers
 // stream 0.29 / 1.18 MB of weights per 16x16-pixel tile and ran at the L2 roofline (6.7 TB/s of L2 reads).
-template <int CC, int COUT, bool RESIDENT, int NKB, bool F16, bool CL = false>
+template <int CC, int COUT, bool RESIDENT, int NKB, bool F16, bool CL = false, bool SPLIT = false>
 __global__ void __launch_bounds__(256, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const ConvHaloParams p) {
     using namespace tc;
-    using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB>;
+    using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB, SPLIT>;
     constexpr int RB = Cfg::RB, AST = Cfg::A_STAGES, BST = Cfg::B_TILES, ACC = Cfg::ACC_STAGES;
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
@@ -133,15 +140,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int y0 = (t2 / p.tiles_x) * 16, x0 = (t2 % p.tiles_x) * 16;
                 for (int ch = 0; ch < p.chunks; ++ch) {
                     mbar_wait(a_empty(as), aph ^ 1);
-                    mbar_arrive_expect_tx(a_full(as), 324 * RB);
+                    mbar_arrive_expect_tx(a_full(as), (SPLIT ? 2 : 1) * 324 * RB);
                     tma_load_4d(smem_base + as * Cfg::PATCH_BYTES, &map_a, a_full(as), ch * CC, x0 - 1, y0 - 1, n);
+                    if (SPLIT) tma_load_4d(smem_base + as * Cfg::PATCH_BYTES + Cfg::PLANE_BYTES, &map_a, a_full(as), ch * CC, x0 - 1, y0 - 1, p.lo_n + n);
                     if (++as == AST) { as = 0; aph ^= 1; }
                     if (!RESIDENT) {
-                        for (int tap = 0; tap < 9; ++tap) {
+                        for (int tap = 0; tap < (SPLIT ? 18 : 9); ++tap) {      // split: (tap, hi), (tap, lo), ... ; lo tiles are rows [COUT, 2 COUT) of the weight map
+                            const int tp = SPLIT ? tap >> 1 : tap, wrow = SPLIT ? (tap & 1) * COUT : 0;
                             mbar_wait(b_empty(bs), bph ^ 1);
                             mbar_arrive_expect_tx(b_full(bs), COUT * RB);
-                            if (!CL) tma_load_2d(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tap * p.cin + ch * CC, 0);
-                            else if ((uint32_t)(bt & 1) == crank) tma_load_2d_mc(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tap * p.cin + ch * CC, 0, (uint16_t)3);
+                            if (!CL) tma_load_2d(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tp * p.cin + ch * CC, wrow);
+                            else if ((uint32_t)(bt & 1) == crank) tma_load_2d_mc(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tp * p.cin + ch * CC, wrow, (uint16_t)3);
                             ++bt;
                             if (++bs == BST) { bs = 0; bph ^= 1; }
                         }
@@ -199,13 +208,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             for (int h = 0; h < 2; ++h)
                                 if (h < nh)
 #pragma unroll
-                                for (int k = 0; k < CC / 16; ++k)
+                                for (int k = 0; k < CC / 16; ++k) {
                                     umma_bf16_lohi(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi,
                                                    idesc, (ch | tap | k) != 0 ? 1u : 0u);
+                                    if (SPLIT)                                                       // lo patch . hi weights
+                                        umma_bf16_lohi(d0 + h * COUT, w_lo + ((Cfg::PLANE_BYTES + 8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4),
+                                                       b_hi, idesc, 1u);
+                                }
                             if (CL) umma_commit_mc(b_empty(bs), (uint16_t)3); else umma_commit(b_empty(bs));
                         }
                         __syncwarp();
                         if (++bs == BST) { bs = 0; bph ^= 1; }
+                        if (SPLIT) {                                                                 // hi patch . lo weights (next ring slot)
+                            mbar_wait(b_full(bs), bph);
+                            tc_fence_after();
+                            const uint32_t bl_lo = (((b_base + bs * Cfg::B_TILE) & 0x3FFFF) >> 4) | (1u << 16);
+                            if (leader) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h)
+                                    if (h < nh)
+#pragma unroll
+                                    for (int k = 0; k < CC / 16; ++k)
+                                        umma_bf16_lohi(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, bl_lo + ((k * 32) >> 4), b_hi, idesc, 1u);
+                                if (CL) umma_commit_mc(b_empty(bs), (uint16_t)3); else umma_commit(b_empty(bs));
+                            }
+                            __syncwarp();
+                            if (++bs == BST) { bs = 0; bph ^= 1; }
+                        }
                     }
                 }
                 if (leader) umma_commit(a_empty(as));
@@ -235,7 +264,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const bool live = oy < p.ho && ox < p.wo && n < p.n;
                 __nv_bfloat16* dst = p.out + (((size_t)n * p.ho + oy) * p.wo + ox) * COUT;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (2 * COUT) + h * COUT;
-                if (p.relu && COUT % 64 == 0) {
+                static_assert(!SPLIT || COUT % 64 == 0, "split halo epilogue handles 64 channels per round trip");
+                if (SPLIT || (p.relu && COUT % 64 == 0)) {
                     // 64 accumulator columns per round trip (two tcgen05.ld.x32, one wait), packed FFMA2 + F2FP.RELU, 128 contiguous
                     // bytes per pixel: the x16 loop below spent ~200 cycles per 16 columns and made the epilogue slower than the UMMAs
 #pragma unroll 1
@@ -244,6 +274,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         tmem_ld32(taddr + c, v);
                         tmem_ld32(taddr + c + 32, v + 32);
                         tmem_ld_wait();
+                        if (SPLIT) {
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {
+                                uint32_t oh[8], ol[8];
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) {
+                                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + 16 * c8 + j);
+                                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + 16 * c8 + j);
+                                    bn_relu_split<F16>(v[16 * c8 + j], v[16 * c8 + j + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[j / 2], ol[j / 2]);
+                                    bn_relu_split<F16>(v[16 * c8 + j + 2], v[16 * c8 + j + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[j / 2 + 1],
+                                                       ol[j / 2 + 1]);
+                                }
+                                if (live) { stg256(dst + c + 16 * c8, oh); stg256(dst + p.out_lo + c + 16 * c8, ol); }
+                            }
+                            continue;
+                        }
                         uint32_t o[32];
 #pragma unroll
                         for (int j = 0; j < 64; j += 4) {

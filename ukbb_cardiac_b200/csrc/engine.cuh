@@ -16,14 +16,14 @@ struct Workspace {          // activation buffers of one sub-batch of slices
     int nb = 0, h = 0, w = 0;
 };
 
-struct Bf16State;           // conv_tc.cu
+struct TcState;             // tc_plan.cuh
 
 struct Engine {
     int device = 0, mode = 0, n_class = 0, sms = 148;
     ConvLayer layers[UKBB_N_CONV];
     Workspace ws;
     PreprocWorkspace pre;
-    Bf16State* tc = nullptr;
+    TcState* tc = nullptr;
     unsigned long long* d_counts = nullptr;
     int counts_cap = 0, counts_n = 0;
     long long launches = 0;
@@ -42,12 +42,13 @@ struct Engine {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_pre[2] = {nullptr, nullptr};
 };
 
-// conv_tc.cu: BF16 tcgen05 path
-int bf16_prepare(Engine* h, const ukbb_fcn_weights* w);
-void bf16_release(Engine* h);
-int forward_bf16(Engine* h, const float* image, int n, int x2, int y2, int x_pre, int y_pre, int x, int y,
-                 uint8_t* labels, float* logits, float* prob, unsigned long long* counts, cudaStream_t st);
+// tc_forward.cu: tcgen05 path (BF16 / FP16 and the split-operand x3 modes)
+int tc_prepare(Engine* h, const ukbb_fcn_weights* w);
+void tc_release(Engine* h);
+int forward_tc(Engine* h, const float* image, int n, int x2, int y2, int x_pre, int y_pre, int x, int y,
+               uint8_t* labels, float* logits, float* prob, unsigned long long* counts, cudaStream_t st);
 
-int debug_conv_bf16(Engine* h, int li, const void* in, int n, int hi, int wi, int level_out, void* out, cudaStream_t st);
+int debug_conv_tc(Engine* h, int li, const void* in, int n, int hi, int wi, int level_out, void* out, cudaStream_t st);
+int debug_read_tc(Engine* h, int which, int level, float* out, long long n_elems, cudaStream_t st);
 
 }  // namespace ukbb

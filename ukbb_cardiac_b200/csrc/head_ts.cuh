@@ -19,6 +19,12 @@
 //     most expensive of the five loads per tile: TMA moves about one box row per cycle, profiles/r1_tma_probe3.log),
 // TMEM columns (512): D0 2 x 32 | B0 3 x 8 | D1 2 x 64 | D2 2 x 64 | A0 2 x 16 | A2 2 x 32 | U 64.
 //
+// SPLIT (x3 modes): every 16-bit operand that carries rounding error is a (hi, lo) pair -- b0, A0, A2, the t_l patches and the
+// weights -- and every product is hi.hi + lo.hi + hi.lo in the same accumulator (U_l is exact, so the upsample terms are
+// U.t_hi + U.t_lo): 3 + 20 + 12 UMMAs per tile instead of 1 + 9 + 4.  TMEM (512): D0 2 x 32 | B0 2 x (8 + 8) | D1 2 x 64 |
+// D2 2 x 64 | A0 1 x (16 + 16) | A2 1 x (32 + 32) | U 64: A0 and A2 are single-buffered (the tensor pipe is the bound here,
+// ~1100 cycles of UMMAs per tile).
+//
 //   S0  D0[128x32] = b0_tile[128x16] . Wsd0^T                      (1 UMMA,  N = 32, A from TMEM)   MMA warp 17
 //   E0  A0 = relu(D0 + shift_sd0) -> 16 bit -> TMEM; b0 of tile i + 2 -> TMEM                          warps 0-3
 //   S1  D1[128x64] = A0 . W_0^T + sum_l U_l . t_l patch             (2 + 7 UMMAs, A from TMEM)       MMA warp 18
@@ -29,74 +35,44 @@
 #pragma once
 #include "tc_common.cuh"
 #include "conv_group.cuh"      // tmem_ld32, TileWalk
-#include "head_mma.cuh"        // HM_* layout constants, HeadMmaMaps, HeadParams
-#include "head_tc.cuh"         // add_relu_pack
+#include "head_common.cuh"     // HM_* layout constants, HeadMaps, HeadParams, add_relu_pack / add_relu_split
 
 namespace ukbb {
 
-namespace tc {
-// D[tmem] (+)= A[tmem] * B[smem]^T : A is [128 lanes][K = 16 as 8 columns of two 16-bit values]
-__device__ __forceinline__ void umma_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .b64 db;\n"
-        "setp.ne.b32 p, %5, 0;\n"
-        "mov.b64 db, {%2, %3};\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
-        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
-        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
-        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-}  // namespace tc
-
 constexpr int H4_E2SETS = 3;                                      // E2 warp sets (4 warps each), tile i -> set i % 3
 constexpr int H4_THREADS = 928;                                   // 29 warps: 0-3 E0, 4-7 E1, 8-19 E2 (3 sets), 20 TMA, 21 S0, 22 / 23 S1 even / odd tiles, 24 S2, 25-28 b0 loaders
-constexpr int H4_STAGES = 10;                                     // input stages (t_l patches): ~2000 cycles of TMA latency at ~700 cycles per tile
 constexpr int H4_D0S = 2;                                         // same_dim0 accumulator stages
-constexpr int H4_B0S = 3;                                         // b0 operand stages in TMEM (8 columns each)
-constexpr int H4_SMEM = H4_STAGES * HM_IN_BYTES + HM_W0 + HM_W1 + HM_WSD + 1024 /*align*/ + 512 /*barriers*/;
+template <bool SPLIT>
+struct HeadTsCfg {
+    static constexpr int STAGES = SPLIT ? 7 : 10;                 // input stages (t_l patches): ~2000 cycles of TMA latency at ~700 cycles per tile
+    static constexpr int IN_BYTES = (SPLIT ? 2 : 1) * HM_IN_PATCHES;   // hi patches | lo patches
+    static constexpr int B0S = SPLIT ? 2 : 3;                     // b0 operand stages in TMEM (8 columns per plane)
+    static constexpr int W_BYTES = (SPLIT ? 2 : 1) * (HM_W0 + HM_W1 + HM_WSD);
+    static constexpr int SMEM = STAGES * IN_BYTES + W_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
 // TMEM columns
 constexpr int H4_D0 = 0, H4_B0 = 64, H4_D1 = 96, H4_D2 = 224, H4_A0 = 352, H4_A2 = 384, H4_U1 = 448, H4_U2 = 472, H4_U3 = 488, H4_U4 = 496;
 
-template <int NC, bool F16>
+template <int NC, bool F16, bool SPLIT = false>
 __global__ void __launch_bounds__(H4_THREADS, 1)
-head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__ HeadParams p) {
+head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadParams p) {
     using namespace tc;
+    using Cfg = HeadTsCfg<SPLIT>;
+    constexpr int H4_STAGES = Cfg::STAGES, H4_B0S = Cfg::B0S, IN_BYTES = Cfg::IN_BYTES;
+    constexpr int PL = SPLIT ? 2 : 1;                              // operand planes
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t in_base = smem_base;
-    const uint32_t w0_base = in_base + H4_STAGES * HM_IN_BYTES;
-    const uint32_t w1_base = w0_base + HM_W0;
-    const uint32_t wsd_base = w1_base + HM_W1;
-    const uint32_t bar_base = wsd_base + HM_WSD;
+    const uint32_t w0_base = in_base + H4_STAGES * IN_BYTES;       // hi [64][32] | lo
+    const uint32_t w1_base = w0_base + PL * HM_W0;                 // hi [64][64] | lo
+    const uint32_t wsd_base = w1_base + PL * HM_W1;                // hi [32][16] | lo
+    const uint32_t bar_base = wsd_base + PL * HM_WSD;
     auto BAR = [&](int i) { return bar_base + 8u * i; };
-    enum { WFULL = 0, UFULL = 1, IN_FULL = 2, IN_EMPTY = IN_FULL + H4_STAGES, D0_FULL = IN_EMPTY + H4_STAGES, D0_EMPTY = D0_FULL + H4_D0S,
-           B0_FULL = D0_EMPTY + H4_D0S, B0_EMPTY = B0_FULL + H4_B0S, A0_FULL = B0_EMPTY + H4_B0S, A0_EMPTY = A0_FULL + 2, D1_FULL = A0_EMPTY + 2, D1_EMPTY = D1_FULL + 2, A2_FULL = D1_EMPTY + 2,
+    enum { WFULL = 0, UFULL = 1, IN_FULL = 2, IN_EMPTY = IN_FULL + 10, D0_FULL = IN_EMPTY + 10, D0_EMPTY = D0_FULL + H4_D0S,
+           B0_FULL = D0_EMPTY + H4_D0S, B0_EMPTY = B0_FULL + 3, A0_FULL = B0_EMPTY + 3, A0_EMPTY = A0_FULL + 2, D1_FULL = A0_EMPTY + 2, D1_EMPTY = D1_FULL + 2, A2_FULL = D1_EMPTY + 2,
            A2_EMPTY = A2_FULL + 2, D2_FULL = A2_EMPTY + 2, D2_EMPTY = D2_FULL + 6, TSLOT = D2_EMPTY + 6 };
     // D2 has two TMEM buffers (tile i -> i & 1) but SIX barrier pairs (tile i -> i % 6): with three E2 warp sets (tile i -> set i % 3) a
     // barrier must belong to one set only -- a parity wait can tell the current phase from the previous one, not from the one before
@@ -106,8 +82,8 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 20 && lane == 0) {
-        const CUtensorMap* m = &maps.s0;
-        for (int i = 0; i < 12; ++i) tma_prefetch_desc(m + i);
+        const CUtensorMap* m = &maps.t1;
+        for (int i = 0; i < 7; ++i) tma_prefetch_desc(m + i);
     }
     if (warp == 21 && lane == 0) {
         mbar_init(BAR(WFULL), 1);
@@ -125,7 +101,7 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
     if (warp == 24) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     // zero the input stages once: the K-padding rows of the t_l patches are never written by TMA and
     // must be finite (they meet zero columns of U_l)
-    for (int i = threadIdx.x; i < H4_STAGES * HM_IN_BYTES / 16; i += H4_THREADS)
+    for (int i = threadIdx.x; i < H4_STAGES * IN_BYTES / 16; i += H4_THREADS)
         reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
@@ -136,40 +112,41 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
     if (warp != 20) griddep_wait();                      // the producer waits after it has issued the weight loads
     const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     auto LO = [](uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); };
-    const bool tracing = (p.dbg & 16) && blockIdx.x == 0 && p.trace != nullptr;
-    auto TRACE = [&](int ev, int tile) { if (tracing && lane == 0 && tile < 64) p.trace[ev * 64 + tile] = clock64(); };
     constexpr uint32_t HI32 = (uint32_t)((8 * 32) >> 4) | (1u << 14) | (6u << 29);
     constexpr uint32_t HI64 = (uint32_t)((8 * 64) >> 4) | (1u << 14) | (4u << 29);
     constexpr uint32_t HI128 = (uint32_t)((8 * 128) >> 4) | (1u << 14) | (2u << 29);
 
     if (warp == 20) {
-        // ===================== TMA producer: the four t_l patch loads of a tile are one warp instruction (lanes 1-4) =====================
+        // ===================== TMA producer: the t_l patch loads of a tile (4, or 8 with the lo planes) are one warp instruction =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(BAR(WFULL), HM_W0 + HM_W1 + HM_WSD);
-            tma_load_2d(wsd_base, &maps.wsd, BAR(WFULL), 0, 0);
-            tma_load_2d(w0_base, &maps.w0, BAR(WFULL), 0, 0);
-            tma_load_2d(w1_base, &maps.w1, BAR(WFULL), 0, 0);
+            mbar_arrive_expect_tx(BAR(WFULL), PL * (HM_W0 + HM_W1 + HM_WSD));
+            for (int pl = 0; pl < PL; ++pl) {                                       // lo weights = rows [cout, 2 cout) of the same maps
+                tma_load_2d(wsd_base + pl * HM_WSD, &maps.wsd, BAR(WFULL), 0, pl * 32);
+                tma_load_2d(w0_base + pl * HM_W0, &maps.w0, BAR(WFULL), 0, pl * 64);
+                tma_load_2d(w1_base + pl * HM_W1, &maps.w1, BAR(WFULL), 0, pl * 64);
+            }
         }
         griddep_wait();
         __syncwarp();
         TileWalk w;
         w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
-        const int l = lane < 5 ? lane : 0;
-        const CUtensorMap* my_map = &maps.s0 + l;                                   // s0, t1, t2, t3, t4 are adjacent
-        const uint32_t my_off = l == 0 ? 0u : l == 1 ? (uint32_t)HM_IN_S0 : l == 2 ? (uint32_t)(HM_IN_S0 + HM_IN_P1)
-                                : l == 3 ? (uint32_t)(HM_IN_S0 + HM_IN_P1 + HM_IN_P2) : (uint32_t)(HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3);
-        const int pb = ((1 << l) - 1) >> 1, back = l > 0 ? 1 : 0;                   // level l patch origin: ((x0 + pb) >> l) - 1
+        const bool loader = lane >= 1 && lane <= 4 * PL;
+        const int l = loader ? ((lane - 1) & 3) + 1 : 1, plane = loader ? (lane - 1) >> 2 : 0;
+        const CUtensorMap* my_map = &maps.t1 + (l - 1);                             // t1, t2, t3, t4 are adjacent
+        const uint32_t my_off = (uint32_t)(plane * HM_IN_PATCHES) +
+                                (l == 1 ? 0u : l == 2 ? (uint32_t)HM_IN_P1 : l == 3 ? (uint32_t)(HM_IN_P1 + HM_IN_P2) : (uint32_t)(HM_IN_P1 + HM_IN_P2 + HM_IN_P3));
+        const int pb = ((1 << l) - 1) >> 1;                                         // level l patch origin: ((x0 + pb) >> l) - 1
+        const int n_off = plane * p.lo_n;
         int s = 0;
         uint32_t ph = 0;
         for (int i = 0; i < my_tiles; ++i) {
             const int y0 = w.ty * 8, x0 = w.tx * 16, n = w.n;
             mbar_wait(BAR(IN_EMPTY + s), ph ^ 1);
-            TRACE(0, i);
-            const uint32_t dst = in_base + s * HM_IN_BYTES;
+            const uint32_t dst = in_base + s * IN_BYTES;
             const uint32_t fullb = BAR(IN_FULL + s);
-            if (lane == 0) { if (p.dbg & 2) mbar_arrive(fullb); else mbar_arrive_expect_tx(fullb, HM_IN_TX - HM_IN_S0); }   // t_l patches only: b0 goes through registers
+            if (lane == 0) mbar_arrive_expect_tx(fullb, PL * HM_IN_PATCH_TX);       // t_l patches only: b0 goes through registers
             __syncwarp();
-            if (lane >= 1 && lane < 5 && !(p.dbg & 2)) tma_load_4d(dst + my_off, my_map, fullb, 0, ((x0 + pb) >> l) - back, ((y0 + pb) >> l) - back, n);
+            if (loader) tma_load_4d(dst + my_off, my_map, fullb, 0, ((x0 + pb) >> l) - 1, ((y0 + pb) >> l) - 1, n_off + n);
             __syncwarp();
             if (++s == H4_STAGES) { s = 0; ph ^= 1; }
             w.next();
@@ -187,9 +164,12 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             mbar_wait(BAR(D0_EMPTY + d), dph ^ 1);
             mbar_wait(BAR(B0_FULL + s), ph);
             tc_fence_after();
-            TRACE(1, i);
             if (leader) {
-                umma_ts_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 8, wsd_lo, HI32, idesc_sd, 0u);
+                umma_ts_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 8 * PL, wsd_lo, HI32, idesc_sd, 0u);
+                if (SPLIT) {
+                    umma_ts_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 16 + 8, wsd_lo, HI32, idesc_sd, 1u);                   // lo . hi
+                    umma_ts_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 16, wsd_lo + (HM_WSD >> 4), HI32, idesc_sd, 1u);       // hi . lo
+                }
                 umma_commit(BAR(B0_EMPTY + s));
                 umma_commit(BAR(D0_FULL + d));
             }
@@ -218,32 +198,38 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             const uint32_t bph = ((uint32_t)i >> 1) & 1u;
             const uint32_t v = (uint32_t)(w.ty & 1);                 // tile-row parity selects the U_4 variant
             mbar_wait(BAR(D1_EMPTY + b), bph ^ 1);
-            mbar_wait(BAR(A0_FULL + b), bph);
+            mbar_wait(BAR(A0_FULL + b), bph);                        // barrier pair i & 1 belongs to this issuer (SPLIT: one A0 buffer, two barrier pairs)
             mbar_wait(BAR(IN_FULL + s), sph);
             tc_fence_after();
-            TRACE(4, i);
             const uint32_t d = tmem_base + H4_D1 + b * 64;
-            const uint32_t in_lo = LO(in_base + s * HM_IN_BYTES);
-            const uint32_t a0 = tmem_base + H4_A0 + b * 16;
+            const uint32_t in_lo = LO(in_base + s * IN_BYTES);
+            const uint32_t a0 = tmem_base + H4_A0 + (SPLIT ? 0 : b * 16);
             if (leader) {
                 umma_ts_lohi(d, a0, w0_lo, HI64, idesc_kk, 0u);
                 umma_ts_lohi(d, a0 + 8, w0_lo + 2, HI64, idesc_kk, 1u);
-                if (!(p.dbg & 4)) {
+                if (SPLIT) {
+                    umma_ts_lohi(d, a0 + 16, w0_lo, HI64, idesc_kk, 1u);                                  // A0_lo . W0_hi
+                    umma_ts_lohi(d, a0 + 24, w0_lo + 2, HI64, idesc_kk, 1u);
+                    umma_ts_lohi(d, a0, w0_lo + (HM_W0 >> 4), HI64, idesc_kk, 1u);                        // A0_hi . W0_lo
+                    umma_ts_lohi(d, a0 + 8, w0_lo + (HM_W0 >> 4) + 2, HI64, idesc_kk, 1u);
+                }
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    umma_ts_lohi(d, tmem_base + H4_U1 + 8 * k, in_lo + ((HM_IN_S0 + k * 2048) >> 4), HI128, idesc_kmn, 1u);
+                for (int pl = 0; pl < PL; ++pl) {                                                         // U_l is exact: U . t_hi + U . t_lo
+                    const uint32_t t_lo = in_lo + ((pl * HM_IN_PATCHES) >> 4);
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    umma_ts_lohi(d, tmem_base + H4_U2 + 8 * k, in_lo + ((HM_IN_S0 + HM_IN_P1 + k * 2048) >> 4), HI128, idesc_kmn, 1u);
-                umma_ts_lohi(d, tmem_base + H4_U3, in_lo + ((HM_IN_S0 + HM_IN_P1 + HM_IN_P2) >> 4), HI128, idesc_kmn, 1u);
-                umma_ts_lohi(d, tmem_base + H4_U4 + 8 * v, in_lo + ((HM_IN_S0 + HM_IN_P1 + HM_IN_P2 + HM_IN_P3) >> 4), HI128, idesc_kmn, 1u);
+                    for (int k = 0; k < 3; ++k)
+                        umma_ts_lohi(d, tmem_base + H4_U1 + 8 * k, t_lo + ((k * 2048) >> 4), HI128, idesc_kmn, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        umma_ts_lohi(d, tmem_base + H4_U2 + 8 * k, t_lo + ((HM_IN_P1 + k * 2048) >> 4), HI128, idesc_kmn, 1u);
+                    umma_ts_lohi(d, tmem_base + H4_U3, t_lo + ((HM_IN_P1 + HM_IN_P2) >> 4), HI128, idesc_kmn, 1u);
+                    umma_ts_lohi(d, tmem_base + H4_U4 + 8 * v, t_lo + ((HM_IN_P1 + HM_IN_P2 + HM_IN_P3) >> 4), HI128, idesc_kmn, 1u);
                 }
                 umma_commit(BAR(IN_EMPTY + s));
                 umma_commit(BAR(A0_EMPTY + b));
                 umma_commit(BAR(D1_FULL + b));
             }
             __syncwarp();
-            TRACE(5, i);
             s += 2;
             if (s >= H4_STAGES) { s -= H4_STAGES; sph ^= 1; }
             w.next();
@@ -259,15 +245,20 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             const int b = i & 1;
             const uint32_t bph = ((uint32_t)i >> 1) & 1u;
             if (i >= 2) mbar_wait(BAR(D2_EMPTY + (i - 2) % 6), (uint32_t)((i - 2) / 6) & 1u);   // the tile that used D2[b] before
-            mbar_wait(BAR(A2_FULL + b), bph);
+            if (SPLIT) mbar_wait(BAR(A2_FULL), (uint32_t)i & 1u); else mbar_wait(BAR(A2_FULL + b), bph);
             tc_fence_after();
-            TRACE(8, i);
             const uint32_t d = tmem_base + H4_D2 + b * 64;
-            const uint32_t a2 = tmem_base + H4_A2 + b * 32;
+            const uint32_t a2 = tmem_base + H4_A2 + (SPLIT ? 0 : b * 32);
             if (leader) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_ts_lohi(d, a2 + 8 * k, w1_lo + 2 * k, HI128, idesc_kk, k != 0 ? 1u : 0u);
-                umma_commit(BAR(A2_EMPTY + b));
+                for (int k = 0; k < 4; ++k) {
+                    umma_ts_lohi(d, a2 + 8 * k, w1_lo + 2 * k, HI128, idesc_kk, k != 0 ? 1u : 0u);
+                    if (SPLIT) {
+                        umma_ts_lohi(d, a2 + 32 + 8 * k, w1_lo + 2 * k, HI128, idesc_kk, 1u);                 // A2_lo . W1_hi
+                        umma_ts_lohi(d, a2 + 8 * k, w1_lo + (HM_W1 >> 4) + 2 * k, HI128, idesc_kk, 1u);       // A2_hi . W1_lo
+                    }
+                }
+                umma_commit(BAR(A2_EMPTY + (SPLIT ? 0 : b)));
                 umma_commit(BAR(D2_FULL + i % 6));
             }
             __syncwarp();
@@ -309,25 +300,43 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, d = i % H4_D0S;
             const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-            mbar_wait(BAR(A0_EMPTY + b), ph ^ 1);
+            if (SPLIT) { if (i >= 1) mbar_wait(BAR(A0_EMPTY + ((i - 1) & 1)), ((uint32_t)(i - 1) >> 1) & 1u); }   // one A0 buffer: S1 of tile i - 1 has consumed it
+            else mbar_wait(BAR(A0_EMPTY + b), ph ^ 1);
             mbar_wait(BAR(D0_FULL + d), (uint32_t)(i / H4_D0S) & 1u);
             tc_fence_after();
-            if (q == 0) TRACE(2, i);
-            uint32_t v[32];
-            tmem_ld32(lane_base + H4_D0 + d * 32, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(D0_EMPTY + d));
-            uint32_t o[16];
+            if (SPLIT) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = add_relu_pack<F16>(v[2 * j], v[2 * j + 1], p.c_shift_sd0[2 * j], p.c_shift_sd0[2 * j + 1]);
-            tmem_st16(lane_base + H4_A0 + b * 16, o);
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[16], oh[8], ol[8];
+                    tmem_ld16(lane_base + H4_D0 + d * 32 + 16 * hf, v);
+                    tmem_ld_wait();
+                    if (hf == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(D0_EMPTY + d));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        add_relu_split<F16>(v[2 * j], v[2 * j + 1], p.c_shift_sd0[16 * hf + 2 * j], p.c_shift_sd0[16 * hf + 2 * j + 1], oh[j], ol[j]);
+                    tmem_st8(lane_base + H4_A0 + 8 * hf, oh);
+                    tmem_st8(lane_base + H4_A0 + 16 + 8 * hf, ol);
+                }
+            } else {
+                uint32_t v[32];
+                tmem_ld32(lane_base + H4_D0 + d * 32, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(D0_EMPTY + d));
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = add_relu_pack<F16>(v[2 * j], v[2 * j + 1], p.c_shift_sd0[2 * j], p.c_shift_sd0[2 * j + 1]);
+                tmem_st16(lane_base + H4_A0 + b * 16, o);
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(A0_FULL + b));
-            if (q == 0) TRACE(3, i);
         }
     } else if (warp >= 25) {
         // ===================== b0 loaders (warps 25-28): the A operand of S0 goes global -> registers -> TMEM =====================
@@ -342,23 +351,39 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
         TileWalk wb;
         wb.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
         auto b0_addr = [&]() { return p.b0 + (((size_t)wb.n * p.h + wb.ty * 8 + pty) * p.w + wb.tx * 16 + ptx) * 2; };
-        uint4 ring_lo[3], ring_hi[3];
+        constexpr int RING = SPLIT ? 2 : 3;                           // register ring = TMEM stages (tiles ahead)
+        uint4 ring[RING][2 * PL];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            ring_lo[u] = make_uint4(0, 0, 0, 0); ring_hi[u] = ring_lo[u];
-            if (u < my_tiles && !(p.dbg & 8)) { const uint4* g = b0_addr(); ring_lo[u] = __ldg(g); ring_hi[u] = __ldg(g + 1); wb.next(); }
+        for (int u = 0; u < RING; ++u) {
+#pragma unroll
+            for (int e = 0; e < 2 * PL; ++e) ring[u][e] = make_uint4(0, 0, 0, 0);
+            if (u < my_tiles) {
+                const uint4* g = b0_addr();
+                ring[u][0] = __ldg(g); ring[u][1] = __ldg(g + 1);
+                if (SPLIT) { ring[u][2] = __ldg(g + p.b0_lo); ring[u][3] = __ldg(g + p.b0_lo + 1); }
+                wb.next();
+            }
         }
-        for (int j0 = 0; j0 < my_tiles; j0 += 3) {
+        for (int j0 = 0; j0 < my_tiles; j0 += RING) {
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
+            for (int u = 0; u < RING; ++u) {
                 const int j = j0 + u;
                 if (j >= my_tiles) break;
-                const int sb = u;                                    // j % 3
+                const int sb = u;                                    // j % RING
                 mbar_wait(BAR(B0_EMPTY + sb), ((uint32_t)(j / H4_B0S) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t t8[8] = {ring_lo[u].x, ring_lo[u].y, ring_lo[u].z, ring_lo[u].w, ring_hi[u].x, ring_hi[u].y, ring_hi[u].z, ring_hi[u].w};
-                tmem_st8(lane_base + H4_B0 + sb * 8, t8);
-                if (j + 3 < my_tiles && !(p.dbg & 8)) { const uint4* g = b0_addr(); ring_lo[u] = __ldg(g); ring_hi[u] = __ldg(g + 1); wb.next(); }
+#pragma unroll
+                for (int pl = 0; pl < PL; ++pl) {
+                    const uint32_t t8[8] = {ring[u][2 * pl].x, ring[u][2 * pl].y, ring[u][2 * pl].z, ring[u][2 * pl].w,
+                                            ring[u][2 * pl + 1].x, ring[u][2 * pl + 1].y, ring[u][2 * pl + 1].z, ring[u][2 * pl + 1].w};
+                    tmem_st8(lane_base + H4_B0 + sb * 8 * PL + 8 * pl, t8);
+                }
+                if (j + RING < my_tiles) {
+                    const uint4* g = b0_addr();
+                    ring[u][0] = __ldg(g); ring[u][1] = __ldg(g + 1);
+                    if (SPLIT) { ring[u][2] = __ldg(g + p.b0_lo); ring[u][3] = __ldg(g + p.b0_lo + 1); }
+                    wb.next();
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -372,30 +397,47 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1;
             const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-            mbar_wait(BAR(A2_EMPTY + b), ph ^ 1);
+            if (SPLIT) mbar_wait(BAR(A2_EMPTY), ((uint32_t)i & 1u) ^ 1u); else mbar_wait(BAR(A2_EMPTY + b), ph ^ 1);
             mbar_wait(BAR(D1_FULL + b), ph);
             tc_fence_after();
-            if (q == 0) TRACE(6, i);
+            if (SPLIT) {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {                          // 32 accumulator columns at a time (register budget of a 29-warp CTA: 64)
-                uint32_t v[32];
-                tmem_ld32(lane_base + H4_D1 + b * 64 + 32 * hf, v);
-                tmem_ld_wait();
-                if (hf == 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(BAR(D1_EMPTY + b));
+                for (int qt = 0; qt < 4; ++qt) {                      // 16 accumulator columns at a time: hi and lo pieces double the live registers
+                    uint32_t v[16], oh[8], ol[8];
+                    tmem_ld16(lane_base + H4_D1 + b * 64 + 16 * qt, v);
+                    tmem_ld_wait();
+                    if (qt == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(D1_EMPTY + b));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        add_relu_split<F16>(v[2 * j], v[2 * j + 1], p.c_shift0[16 * qt + 2 * j], p.c_shift0[16 * qt + 2 * j + 1], oh[j], ol[j]);
+                    tmem_st8(lane_base + H4_A2 + 8 * qt, oh);
+                    tmem_st8(lane_base + H4_A2 + 32 + 8 * qt, ol);
                 }
-                uint32_t o[16];
+            } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = add_relu_pack<F16>(v[2 * j], v[2 * j + 1], p.c_shift0[32 * hf + 2 * j], p.c_shift0[32 * hf + 2 * j + 1]);
-                tmem_st16(lane_base + H4_A2 + b * 32 + 16 * hf, o);
+                for (int hf = 0; hf < 2; ++hf) {                      // 32 accumulator columns at a time (register budget of a 29-warp CTA: 64)
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + H4_D1 + b * 64 + 32 * hf, v);
+                    tmem_ld_wait();
+                    if (hf == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(D1_EMPTY + b));
+                    }
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = add_relu_pack<F16>(v[2 * j], v[2 * j + 1], p.c_shift0[32 * hf + 2 * j], p.c_shift0[32 * hf + 2 * j + 1]);
+                    tmem_st16(lane_base + H4_A2 + b * 32 + 16 * hf, o);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
-            if (q == 0) TRACE(7, i);
+            if (lane == 0) mbar_arrive(BAR(A2_FULL + (SPLIT ? 0 : b)));
         }
     } else if (warp < 20) {
         // ===================== E2: FP32 class scores -> labels; three warp sets (8-11, 12-15, 16-19), tile i -> set i % 3 =====================
@@ -410,7 +452,6 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
             const uint32_t ph = ((uint32_t)i >> 1) & 1u;
             mbar_wait(BAR(D2_FULL + i % 6), (uint32_t)(i / 6) & 1u);
             tc_fence_after();
-            if (q == 0) TRACE(9, i);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + H4_D2 + b * 64;
             // class scores in FP32: relu(d + s) . w = max(d, -s) . w + s . w, and the constant s . w is part of the bias
             // (host, float64), so an input channel costs one FMNMX and one packed FFMA2 per PAIR of classes; weights,
@@ -433,7 +474,6 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
 #pragma unroll
                 for (int kk = 0; kk < 32; ++kk) {
                     const int k = 32 * hf + kk;
-                    if (k == 8 && (p.dbg & 1)) break;                                             // experiment: how much of the tile time is E2 issue?
                     const float f = fmaxf(__uint_as_float(v[kk]), p.c_nshift1[k]);
                     uint64_t ff;
                     asm("mov.b64 %0, {%1, %1};" : "=l"(ff) : "f"(f));
@@ -495,7 +535,6 @@ head_ts_kernel(const __grid_constant__ HeadMmaMaps maps, const __grid_constant__
                     }
                 }
             }
-            if (q == 0) TRACE(10, i);
             w.next();
         }
     }

@@ -12,6 +12,11 @@
 // the four levels share one launch: tiles are ordered level 4, 3, 2, 1 and dealt round-robin, so the
 // few deep-level tiles (large K) overlap with the many shallow ones.  All weights (46 KB) are resident.
 // HBM traffic per SA slice: 0.5 MB read + 0.85 MB written; the kernel is bound by that, not by the tensor pipe.
+//
+// SPLIT (x3 modes): inputs, weights, s_l and t_l are (hi, lo) pairs of 16-bit values and every product is hi.hi + lo.hi + hi.lo.
+// Shared memory then holds both weight sets (96 KB) and a ring of four (hi, lo) input slots, so A1 = s_l moves to TENSOR MEMORY
+// (tcgen05.st, [tmem] A operand of S1, as in head_ts.cuh) and t_l is written with direct 256-bit stores: one pixel's 64 channels
+// are 128 contiguous bytes per plane and consecutive threads own consecutive pixels.
 #pragma once
 #include "tc_common.cuh"
 #include "conv_group.cuh"      // tmem_ld32, bn_relu_pack, bulk-group helpers
@@ -29,17 +34,25 @@ struct SideParams {
     int tile_start[5];          // k-th level in processing order (level 4 - k) owns tiles [tile_start[k], tile_start[k+1])
     const float* scale[4];      // same_dim BN scale / shift, index = level - 1
     const float* shift[4];
+    // split modes
+    int rows[4];                // pixels of level l in this call (index = level - 1)
+    int lo_row[4];              // row of the lo plane in the input map of level l (= pixels of the plan's capacity)
+    uint32_t* t[4];             // t_l hi plane [pixels][64] as 32-bit words
+    long long t_lo[4];          // offset of the lo plane in 32-bit words
 };
 
 constexpr int SD_THREADS = 384;
 constexpr int SD_SLOT = 128 * 128;                      // one 64-channel chunk of 128 pixels
 constexpr int SD_SLOTS = 7;
+constexpr int SD_SLOTS_SPLIT = 4;                       // (hi, lo) slot pairs
 __host__ __device__ constexpr int sd_wsd_off(int l) { return l == 1 ? 0 : 4096 << (l - 2); }   // offsets 0, 4 K, 8 K, 16 K.  W_sd_l: 32 rows x Cin_l, as Cin_l/64 chunks of [32][128 B] (level 1: [32][64 B])
 constexpr int SD_WSD_BYTES = 32768;
 constexpr int SD_WL_BYTES = 4 * 4096;                   // W_l: [64][32] each
 constexpr int SD_A1 = 128 * 64, SD_OUT = 128 * 128;
 constexpr int SD_SMEM = SD_SLOTS * SD_SLOT + SD_WSD_BYTES + SD_WL_BYTES + 2 * SD_A1 + 2 * SD_OUT + 1024 /*align*/ + 256 /*barriers*/ +
                         4 * 64 * 4 /*scale, shift*/;
+constexpr int SD_SMEM_SPLIT = SD_SLOTS_SPLIT * 2 * SD_SLOT + 2 * (SD_WSD_BYTES + SD_WL_BYTES) + 1024 + 256 + 4 * 64 * 4;
+static_assert(SD_SMEM_SPLIT <= 227 * 1024, "shared memory budget");
 
 namespace tc {
 __device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src, int c0, int c1) {
@@ -54,30 +67,38 @@ __device__ __forceinline__ uint32_t plain_pack(uint32_t a0, uint32_t a1) {
     else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(a1)), "f"(__uint_as_float(a0)));
     return r;
 }
+// two FP32 values -> hi and lo 16-bit pieces, no activation
+template <bool F16>
+__device__ __forceinline__ void plain_split(uint32_t a0, uint32_t a1, uint32_t& hi, uint32_t& lo) {
+    hi = plain_pack<F16>(a0, a1);
+    const float2 h = unpack16t<F16>(hi);
+    lo = plain_pack<F16>(__float_as_uint(__uint_as_float(a0) - h.x), __float_as_uint(__uint_as_float(a1) - h.y));
+}
 }  // namespace tc
 
-template <bool F16>
+template <bool F16, bool SPLIT = false>
 __global__ void __launch_bounds__(SD_THREADS, 1)
 side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ SideParams p) {
     using namespace tc;
+    constexpr int SLOTS = SPLIT ? SD_SLOTS_SPLIT : SD_SLOTS, SLOT_BYTES = (SPLIT ? 2 : 1) * SD_SLOT, PL = SPLIT ? 2 : 1;
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t ring_base = smem_base;
-    const uint32_t wsd_base = ring_base + SD_SLOTS * SD_SLOT;
-    const uint32_t wl_base = wsd_base + SD_WSD_BYTES;
-    const uint32_t a1_base = wl_base + SD_WL_BYTES;
-    const uint32_t out_base = a1_base + 2 * SD_A1;
-    const uint32_t bar_base = out_base + 2 * SD_OUT;
+    const uint32_t wsd_base = ring_base + SLOTS * SLOT_BYTES;            // hi set | lo set
+    const uint32_t wl_base = wsd_base + PL * SD_WSD_BYTES;               // hi set | lo set
+    const uint32_t a1_base = wl_base + PL * SD_WL_BYTES;                 // (not SPLIT) s_l tile as the A operand of S1
+    const uint32_t out_base = a1_base + (SPLIT ? 0 : 2 * SD_A1);         // (not SPLIT) staging tiles of the TMA store
+    const uint32_t bar_base = out_base + (SPLIT ? 0 : 2 * SD_OUT);
     auto BAR = [&](int i) { return bar_base + 8u * i; };
-    enum { WFULL = 0, IN_FULL = 1, IN_EMPTY = IN_FULL + SD_SLOTS, D0_FULL = IN_EMPTY + SD_SLOTS, D0_EMPTY = D0_FULL + 2,
+    enum { WFULL = 0, IN_FULL = 1, IN_EMPTY = IN_FULL + SD_SLOTS, D0_FULL = IN_EMPTY + SD_SLOTS, D0_EMPTY = D0_FULL + 2,   // (SLOTS <= SD_SLOTS)
            A1_FULL = D0_EMPTY + 2, A1_EMPTY = A1_FULL + 2, D1_FULL = A1_EMPTY + 2, D1_EMPTY = D1_FULL + 2, TSLOT = D1_EMPTY + 2 };
     static_assert((TSLOT + 1) * 8 <= 256, "barrier area");
     const uint32_t tmem_slot = BAR(TSLOT);
     float* s_scale = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 256);      // [4][32]
     float* s_shift = s_scale + 128;
-    constexpr int D0_COL = 0, D1_COL = 64;                 // TMEM columns: 2 x 32, 2 x 64
+    constexpr int D0_COL = 0, D1_COL = 64, A1_COL = 192;  // TMEM columns: 2 x 32, 2 x 64, (SPLIT) A1 2 x (16 hi + 16 lo)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.tile_start[4];
@@ -88,7 +109,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
     }
     if (warp == 1 && lane == 0) {
         mbar_init(BAR(WFULL), 1);
-        for (int s = 0; s < SD_SLOTS; ++s) { mbar_init(BAR(IN_FULL + s), 1); mbar_init(BAR(IN_EMPTY + s), 1); }
+        for (int s = 0; s < SLOTS; ++s) { mbar_init(BAR(IN_FULL + s), 1); mbar_init(BAR(IN_EMPTY + s), 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(BAR(D0_FULL + b), 1); mbar_init(BAR(D0_EMPTY + b), 4);
             mbar_init(BAR(A1_FULL + b), 4); mbar_init(BAR(A1_EMPTY + b), 1);
@@ -116,11 +137,14 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(BAR(WFULL), 32 * 64 + 32 * 128 * 7 + SD_WL_BYTES);
-            tma_load_2d(wsd_base + sd_wsd_off(1), &maps.wsd[0], BAR(WFULL), 0, 0);
-            for (int l = 2; l <= 4; ++l)
-                for (int c = 0; c < (1 << (l - 2)); ++c) tma_load_2d(wsd_base + sd_wsd_off(l) + c * 4096, &maps.wsd[l - 1], BAR(WFULL), c * 64, 0);
-            for (int l = 1; l <= 4; ++l) tma_load_2d(wl_base + (l - 1) * 4096, &maps.w0, BAR(WFULL), 32 * l, 0);
+            mbar_arrive_expect_tx(BAR(WFULL), PL * (32 * 64 + 32 * 128 * 7 + SD_WL_BYTES));
+            for (int pl = 0; pl < PL; ++pl) {                // lo weights = rows [cout, 2 cout) of the same maps
+                tma_load_2d(wsd_base + pl * SD_WSD_BYTES + sd_wsd_off(1), &maps.wsd[0], BAR(WFULL), 0, 32 * pl);
+                for (int l = 2; l <= 4; ++l)
+                    for (int c = 0; c < (1 << (l - 2)); ++c)
+                        tma_load_2d(wsd_base + pl * SD_WSD_BYTES + sd_wsd_off(l) + c * 4096, &maps.wsd[l - 1], BAR(WFULL), c * 64, 32 * pl);
+                for (int l = 1; l <= 4; ++l) tma_load_2d(wl_base + pl * SD_WL_BYTES + (l - 1) * 4096, &maps.w0, BAR(WFULL), 32 * l, 64 * pl);
+            }
             griddep_wait();
             int slot = 0;
             uint32_t ph = 0;
@@ -132,9 +156,10 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
                 const uint32_t bytes = l == 1 ? 128 * 64 : 128 * 128;
                 for (int c = 0; c < chunks; ++c) {
                     mbar_wait(BAR(IN_EMPTY + slot), ph ^ 1);
-                    mbar_arrive_expect_tx(BAR(IN_FULL + slot), bytes);
-                    tma_load_2d(ring_base + slot * SD_SLOT, &maps.in[l - 1], BAR(IN_FULL + slot), c * 64, row0);
-                    if (++slot == SD_SLOTS) { slot = 0; ph ^= 1; }
+                    mbar_arrive_expect_tx(BAR(IN_FULL + slot), PL * bytes);
+                    tma_load_2d(ring_base + slot * SLOT_BYTES, &maps.in[l - 1], BAR(IN_FULL + slot), c * 64, row0);
+                    if (SPLIT) tma_load_2d(ring_base + slot * SLOT_BYTES + SD_SLOT, &maps.in[l - 1], BAR(IN_FULL + slot), c * 64, p.lo_row[l - 1] + row0);
+                    if (++slot == SLOTS) { slot = 0; ph ^= 1; }
                 }
             }
         }
@@ -160,15 +185,20 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
             for (int c = 0; c < chunks; ++c) {
                 mbar_wait(BAR(IN_FULL + slot), ph);
                 tc_fence_after();
-                const uint32_t a_lo = LO(ring_base + slot * SD_SLOT);
+                const uint32_t a_lo = LO(ring_base + slot * SLOT_BYTES);
                 if (leader) {
-                    for (int k = 0; k < ksteps; ++k)
+                    for (int k = 0; k < ksteps; ++k) {
                         umma_bf16_lohi(d, a_lo + 2 * k, hi, w_lo + c * (4096 >> 4) + 2 * k, hi, idesc, (c | k) != 0 ? 1u : 0u);
+                        if (SPLIT) {
+                            umma_bf16_lohi(d, a_lo + (SD_SLOT >> 4) + 2 * k, hi, w_lo + c * (4096 >> 4) + 2 * k, hi, idesc, 1u);              // lo . hi
+                            umma_bf16_lohi(d, a_lo + 2 * k, hi, w_lo + (SD_WSD_BYTES >> 4) + c * (4096 >> 4) + 2 * k, hi, idesc, 1u);        // hi . lo
+                        }
+                    }
                     umma_commit(BAR(IN_EMPTY + slot));
                     if (c == chunks - 1) umma_commit(BAR(D0_FULL + b));
                 }
                 __syncwarp();
-                if (++slot == SD_SLOTS) { slot = 0; ph ^= 1; }
+                if (++slot == SLOTS) { slot = 0; ph ^= 1; }
             }
         }
     } else if (warp == 2) {
@@ -188,8 +218,17 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
             const uint32_t d = tmem_base + D1_COL + b * 64;
             const uint32_t a_lo = LO(a1_base + b * SD_A1), w_lo = LO(wl_base + (l - 1) * 4096);
             if (leader) {
+                if (SPLIT) {                                    // A1 = (hi 16 columns | lo 16 columns) in tensor memory
+                    const uint32_t a1 = tmem_base + A1_COL + b * 32;
+                    for (int k = 0; k < 2; ++k) {
+                        umma_ts_lohi(d, a1 + 8 * k, w_lo + 2 * k, HI64, idesc, k != 0 ? 1u : 0u);
+                        umma_ts_lohi(d, a1 + 16 + 8 * k, w_lo + 2 * k, HI64, idesc, 1u);
+                        umma_ts_lohi(d, a1 + 8 * k, w_lo + (SD_WL_BYTES >> 4) + 2 * k, HI64, idesc, 1u);
+                    }
+                } else {
                 umma_bf16_lohi(d, a_lo, HI64, w_lo, HI64, idesc, 0u);
                 umma_bf16_lohi(d, a_lo + 2, HI64, w_lo + 2, HI64, idesc, 1u);
+                }
                 umma_commit(BAR(A1_EMPTY + b));
                 umma_commit(BAR(D1_FULL + b));
             }
@@ -215,6 +254,27 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
             mbar_wait(BAR(A1_EMPTY + b), ph ^ 1u);          // S1 of tile i - 2 has consumed A1[b]
             const float* sc = s_scale + (l - 1) * 32;
             const float* sh = s_shift + (l - 1) * 32;
+            if (SPLIT) {
+                tc_fence_after();
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t oh[8], ol[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 sc0 = *reinterpret_cast<const float4*>(sc + 16 * hf + j), sh0 = *reinterpret_cast<const float4*>(sh + 16 * hf + j);
+                        bn_relu_split<F16>(v[16 * hf + j], v[16 * hf + j + 1], make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y), oh[j / 2], ol[j / 2]);
+                        bn_relu_split<F16>(v[16 * hf + j + 2], v[16 * hf + j + 3], make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w), oh[j / 2 + 1],
+                                           ol[j / 2 + 1]);
+                    }
+                    tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + A1_COL + b * 32 + 8 * hf, oh);
+                    tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + A1_COL + b * 32 + 16 + 8 * hf, ol);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(A1_FULL + b));
+                continue;
+            }
             const uint32_t row = a1_base + b * SD_A1 + r * 64;
             const uint32_t sw = ((uint32_t)r >> 1) & 3u;
 #pragma unroll
@@ -254,6 +314,19 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(D1_EMPTY + b));
+            if (SPLIT) {
+                const int prow = row0 + r;
+                uint32_t* dst = p.t[l - 1] + (size_t)prow * 32;
+                const bool live = prow < p.rows[l - 1];
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t oh[8], ol[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) plain_split<F16>(v[16 * c8 + 2 * j], v[16 * c8 + 2 * j + 1], oh[j], ol[j]);
+                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.t_lo[l - 1] + 8 * c8, ol); }
+                }
+                continue;
+            }
             // staging set b was read by the store of tile i - 2, which the issuer waited for before the last barrier
             const uint32_t row = out_base + b * SD_OUT + r * 128;
 #pragma unroll
@@ -271,7 +344,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
                 bulk_commit();
             }
         }
-        if (issuer) bulk_wait<0>();
+        if (issuer && !SPLIT) bulk_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
