@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("UKBB_BENCH_MODE", "bf16"), choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--mode", default=os.environ.get("UKBB_BENCH_MODE", "fp16x3"), choices=["fp16x3", "bf16x3", "bf16", "fp16", "fp32"])
     ap.add_argument("--subjects", type=int, default=None, help="SA subjects per GPU per step (default 256 bf16, 2 fp32)")
     ap.add_argument("--ref-frames", type=int, default=20, help="frames per step of the reference arm (20 frames = 200 slices, ~5 s of CPU work)")
     ap.add_argument("--cpu-frames", type=int, default=50, help="frames in the cpu_baseline sample (0 = skip); 50 = one whole subject, ~14 s")
@@ -306,7 +306,7 @@ def main():
             "metric": "SA FCN 192x208 slices/sec", "value": value, "unit": "slices/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.mode], "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32", "fp16x3": "f16x3", "bf16x3": "bf16x3"}[args.mode], "data": "synthetic",
             "config": {"workload": "%d synthetic SA subjects (192x208x10x50, 500 slices each) per GPU per step" % S,
                        "subjects_per_gpu": S, "global_subjects": S * world, "mode": args.mode, "n_class": 4,
                        "l2_policy": "inputs larger than L2: %d distinct 80 MB volumes cycled" % pool,

@@ -22,8 +22,8 @@
 // SPLIT (x3 modes): every 16-bit operand that carries rounding error is a (hi, lo) pair -- b0, A0, A2, the t_l patches and the
 // weights -- and every product is hi.hi + lo.hi + hi.lo in the same accumulator (U_l is exact, so the upsample terms are
 // U.t_hi + U.t_lo): 3 + 20 + 12 UMMAs per tile instead of 1 + 9 + 4.  TMEM (512): D0 2 x 32 | B0 2 x (8 + 8) | D1 2 x 64 |
-// D2 2 x 64 | A0 1 x (16 + 16) | A2 1 x (32 + 32) | U 64: A0 and A2 are single-buffered (the tensor pipe is the bound here,
-// ~1100 cycles of UMMAs per tile).
+// D2 2 x 64 | A0 2 x (16 + 16) | A2 1 x (32 + 32) | U 64 with D0 single-buffered: the chain E0 -> A0 -> S1 (20 UMMAs) is the long
+// one (a single A0 buffer measured 2350 cycles per tile), S0 -> D0 -> E0's tcgen05.ld is short.
 //
 //   S0  D0[128x32] = b0_tile[128x16] . Wsd0^T                      (1 UMMA,  N = 32, A from TMEM)   MMA warp 17
 //   E0  A0 = relu(D0 + shift_sd0) -> 16 bit -> TMEM; b0 of tile i + 2 -> TMEM                          warps 0-3
@@ -39,11 +39,15 @@
 
 namespace ukbb {
 
-constexpr int H4_E2SETS = 3;                                      // E2 warp sets (4 warps each), tile i -> set i % 3
 constexpr int H4_THREADS = 928;                                   // 29 warps: 0-3 E0, 4-7 E1, 8-19 E2 (3 sets), 20 TMA, 21 S0, 22 / 23 S1 even / odd tiles, 24 S2, 25-28 b0 loaders
-constexpr int H4_D0S = 2;                                         // same_dim0 accumulator stages
+                                                                  // (SPLIT: warps 16-19 are a second E1 set -- the hi / lo split of 64 channels is
+                                                                  //  ~450 instructions per pixel row -- and E2 runs on two sets)
 template <bool SPLIT>
 struct HeadTsCfg {
+    static constexpr int D0S = SPLIT ? 1 : 2;                     // same_dim0 accumulator stages
+    // TMEM columns
+    static constexpr int D0 = 0, A0 = SPLIT ? 32 : 352, B0 = SPLIT ? 96 : 64, D1 = SPLIT ? 128 : 96, D2 = SPLIT ? 256 : 224, A2 = 384, U1 = 448, U2 = 472,
+                         U3 = 488, U4 = 496;
     static constexpr int STAGES = SPLIT ? 7 : 10;                 // input stages (t_l patches): ~2000 cycles of TMA latency at ~700 cycles per tile
     static constexpr int IN_BYTES = (SPLIT ? 2 : 1) * HM_IN_PATCHES;   // hi patches | lo patches
     static constexpr int B0S = SPLIT ? 2 : 3;                     // b0 operand stages in TMEM (8 columns per plane)
@@ -51,16 +55,18 @@ struct HeadTsCfg {
     static constexpr int SMEM = STAGES * IN_BYTES + W_BYTES + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
-// TMEM columns
-constexpr int H4_D0 = 0, H4_B0 = 64, H4_D1 = 96, H4_D2 = 224, H4_A0 = 352, H4_A2 = 384, H4_U1 = 448, H4_U2 = 472, H4_U3 = 488, H4_U4 = 496;
 
 template <int NC, bool F16, bool SPLIT = false>
 __global__ void __launch_bounds__(H4_THREADS, 1)
 head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadParams p) {
     using namespace tc;
     using Cfg = HeadTsCfg<SPLIT>;
-    constexpr int H4_STAGES = Cfg::STAGES, H4_B0S = Cfg::B0S, IN_BYTES = Cfg::IN_BYTES;
+    constexpr int H4_STAGES = Cfg::STAGES, H4_B0S = Cfg::B0S, IN_BYTES = Cfg::IN_BYTES, H4_D0S = Cfg::D0S;
+    constexpr int H4_D0 = Cfg::D0, H4_B0 = Cfg::B0, H4_D1 = Cfg::D1, H4_D2 = Cfg::D2, H4_A0 = Cfg::A0, H4_A2 = Cfg::A2, H4_U1 = Cfg::U1, H4_U2 = Cfg::U2,
+                  H4_U3 = Cfg::U3, H4_U4 = Cfg::U4;
     constexpr int PL = SPLIT ? 2 : 1;                              // operand planes
+    constexpr int H4_E2SETS = SPLIT ? 2 : 3;                       // E2 warp sets (4 warps each), tile i -> set i % H4_E2SETS
+    constexpr int E1SETS = SPLIT ? 2 : 1;                          // E1 warp sets: set e converts accumulator columns [32 e, 32 e + 32)
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -71,8 +77,8 @@ head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
     const uint32_t wsd_base = w1_base + PL * HM_W1;                // hi [32][16] | lo
     const uint32_t bar_base = wsd_base + PL * HM_WSD;
     auto BAR = [&](int i) { return bar_base + 8u * i; };
-    enum { WFULL = 0, UFULL = 1, IN_FULL = 2, IN_EMPTY = IN_FULL + 10, D0_FULL = IN_EMPTY + 10, D0_EMPTY = D0_FULL + H4_D0S,
-           B0_FULL = D0_EMPTY + H4_D0S, B0_EMPTY = B0_FULL + 3, A0_FULL = B0_EMPTY + 3, A0_EMPTY = A0_FULL + 2, D1_FULL = A0_EMPTY + 2, D1_EMPTY = D1_FULL + 2, A2_FULL = D1_EMPTY + 2,
+    enum { WFULL = 0, UFULL = 1, IN_FULL = 2, IN_EMPTY = IN_FULL + 10, D0_FULL = IN_EMPTY + 10, D0_EMPTY = D0_FULL + 2,
+           B0_FULL = D0_EMPTY + 2, B0_EMPTY = B0_FULL + 3, A0_FULL = B0_EMPTY + 3, A0_EMPTY = A0_FULL + 2, D1_FULL = A0_EMPTY + 2, D1_EMPTY = D1_FULL + 2, A2_FULL = D1_EMPTY + 2,
            A2_EMPTY = A2_FULL + 2, D2_FULL = A2_EMPTY + 2, D2_EMPTY = D2_FULL + 6, TSLOT = D2_EMPTY + 6 };
     // D2 has two TMEM buffers (tile i -> i & 1) but SIX barrier pairs (tile i -> i % 6): with three E2 warp sets (tile i -> set i % 3) a
     // barrier must belong to one set only -- a parity wait can tell the current phase from the previous one, not from the one before
@@ -92,8 +98,8 @@ head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
         for (int d = 0; d < H4_D0S; ++d) { mbar_init(BAR(D0_FULL + d), 1); mbar_init(BAR(D0_EMPTY + d), 4); }
         for (int d = 0; d < H4_B0S; ++d) { mbar_init(BAR(B0_FULL + d), 4); mbar_init(BAR(B0_EMPTY + d), 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(BAR(A0_FULL + b), 4); mbar_init(BAR(A0_EMPTY + b), 1); mbar_init(BAR(D1_FULL + b), 1); mbar_init(BAR(D1_EMPTY + b), 4);
-            mbar_init(BAR(A2_FULL + b), 4); mbar_init(BAR(A2_EMPTY + b), 1);
+            mbar_init(BAR(A0_FULL + b), 4); mbar_init(BAR(A0_EMPTY + b), 1); mbar_init(BAR(D1_FULL + b), 1); mbar_init(BAR(D1_EMPTY + b), 4 * E1SETS);
+            mbar_init(BAR(A2_FULL + b), 4 * E1SETS); mbar_init(BAR(A2_EMPTY + b), 1);
         }
         for (int k = 0; k < 6; ++k) { mbar_init(BAR(D2_FULL + k), 1); mbar_init(BAR(D2_EMPTY + k), 4); }
         fence_barrier_init();
@@ -198,12 +204,12 @@ head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
             const uint32_t bph = ((uint32_t)i >> 1) & 1u;
             const uint32_t v = (uint32_t)(w.ty & 1);                 // tile-row parity selects the U_4 variant
             mbar_wait(BAR(D1_EMPTY + b), bph ^ 1);
-            mbar_wait(BAR(A0_FULL + b), bph);                        // barrier pair i & 1 belongs to this issuer (SPLIT: one A0 buffer, two barrier pairs)
+            mbar_wait(BAR(A0_FULL + b), bph);
             mbar_wait(BAR(IN_FULL + s), sph);
             tc_fence_after();
             const uint32_t d = tmem_base + H4_D1 + b * 64;
             const uint32_t in_lo = LO(in_base + s * IN_BYTES);
-            const uint32_t a0 = tmem_base + H4_A0 + (SPLIT ? 0 : b * 16);
+            const uint32_t a0 = tmem_base + H4_A0 + b * 16 * PL;
             if (leader) {
                 umma_ts_lohi(d, a0, w0_lo, HI64, idesc_kk, 0u);
                 umma_ts_lohi(d, a0 + 8, w0_lo + 2, HI64, idesc_kk, 1u);
@@ -300,26 +306,24 @@ head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, d = i % H4_D0S;
             const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-            if (SPLIT) { if (i >= 1) mbar_wait(BAR(A0_EMPTY + ((i - 1) & 1)), ((uint32_t)(i - 1) >> 1) & 1u); }   // one A0 buffer: S1 of tile i - 1 has consumed it
-            else mbar_wait(BAR(A0_EMPTY + b), ph ^ 1);
+            mbar_wait(BAR(A0_EMPTY + b), ph ^ 1);
             mbar_wait(BAR(D0_FULL + d), (uint32_t)(i / H4_D0S) & 1u);
             tc_fence_after();
             if (SPLIT) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + H4_D0 + d * 32, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(D0_EMPTY + d));        // D0 is single-buffered here: release it before the conversion
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[16], oh[8], ol[8];
-                    tmem_ld16(lane_base + H4_D0 + d * 32 + 16 * hf, v);
-                    tmem_ld_wait();
-                    if (hf == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR(D0_EMPTY + d));
-                    }
+                    uint32_t oh[8], ol[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        add_relu_split<F16>(v[2 * j], v[2 * j + 1], p.c_shift_sd0[16 * hf + 2 * j], p.c_shift_sd0[16 * hf + 2 * j + 1], oh[j], ol[j]);
-                    tmem_st8(lane_base + H4_A0 + 8 * hf, oh);
-                    tmem_st8(lane_base + H4_A0 + 16 + 8 * hf, ol);
+                        add_relu_split<F16>(v[16 * hf + 2 * j], v[16 * hf + 2 * j + 1], p.c_shift_sd0[16 * hf + 2 * j], p.c_shift_sd0[16 * hf + 2 * j + 1], oh[j], ol[j]);
+                    tmem_st8(lane_base + H4_A0 + b * 32 + 8 * hf, oh);
+                    tmem_st8(lane_base + H4_A0 + b * 32 + 16 + 8 * hf, ol);
                 }
             } else {
                 uint32_t v[32];
@@ -390,33 +394,41 @@ head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
                 if (lane == 0) mbar_arrive(BAR(B0_FULL + sb));
             }
         }
-    } else if (warp < 8) {
-        // ===================== E1 (D1 -> A2), warps 4-7 =====================
+    } else if (warp < 8 || (SPLIT && warp >= 16 && warp < 20)) {
+        // ===================== E1 (D1 -> A2), warps 4-7 (SPLIT: and warps 16-19 for the upper 32 columns) =====================
         const int q = warp & 3;
+        const int e1 = warp < 8 ? 0 : 1;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1;
             const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-            if (SPLIT) mbar_wait(BAR(A2_EMPTY), ((uint32_t)i & 1u) ^ 1u); else mbar_wait(BAR(A2_EMPTY + b), ph ^ 1);
+            if (!SPLIT) mbar_wait(BAR(A2_EMPTY + b), ph ^ 1);
             mbar_wait(BAR(D1_FULL + b), ph);
             tc_fence_after();
             if (SPLIT) {
+                // A2 is single-buffered: convert this set's 32 accumulator columns into registers FIRST, wait for S2 of the previous
+                // tile to release A2 only then, and store -- the loop S2 -> A2_EMPTY -> E1 -> A2_FULL -> S2 then holds four tcgen05.st
+                // instead of the whole conversion.
+                uint32_t oh[16], ol[16];
 #pragma unroll
-                for (int qt = 0; qt < 4; ++qt) {                      // 16 accumulator columns at a time: hi and lo pieces double the live registers
-                    uint32_t v[16], oh[8], ol[8];
+                for (int qq = 0; qq < 2; ++qq) {                      // 16 accumulator columns at a time (register budget: 64)
+                    const int qt = 2 * e1 + qq;
+                    uint32_t v[16];
                     tmem_ld16(lane_base + H4_D1 + b * 64 + 16 * qt, v);
                     tmem_ld_wait();
-                    if (qt == 3) {
+                    if (qq == 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(BAR(D1_EMPTY + b));
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        add_relu_split<F16>(v[2 * j], v[2 * j + 1], p.c_shift0[16 * qt + 2 * j], p.c_shift0[16 * qt + 2 * j + 1], oh[j], ol[j]);
-                    tmem_st8(lane_base + H4_A2 + 8 * qt, oh);
-                    tmem_st8(lane_base + H4_A2 + 32 + 8 * qt, ol);
+                        add_relu_split<F16>(v[2 * j], v[2 * j + 1], p.c_shift0[16 * qt + 2 * j], p.c_shift0[16 * qt + 2 * j + 1], oh[8 * qq + j], ol[8 * qq + j]);
                 }
+                mbar_wait(BAR(A2_EMPTY), ((uint32_t)i & 1u) ^ 1u);
+                tc_fence_after();
+                tmem_st16(lane_base + H4_A2 + 16 * e1, oh);
+                tmem_st16(lane_base + H4_A2 + 32 + 16 * e1, ol);
             } else {
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {                      // 32 accumulator columns at a time (register budget of a 29-warp CTA: 64)
@@ -440,7 +452,7 @@ head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
             if (lane == 0) mbar_arrive(BAR(A2_FULL + (SPLIT ? 0 : b)));
         }
     } else if (warp < 20) {
-        // ===================== E2: FP32 class scores -> labels; three warp sets (8-11, 12-15, 16-19), tile i -> set i % 3 =====================
+        // ===================== E2: FP32 class scores -> labels; warp sets 8-11, 12-15 (and 16-19 when not SPLIT), tile i -> set i % H4_E2SETS =====================
         const int set = (warp - 8) >> 2;
         const int q = warp & 3;
         const int r = q * 32 + lane;

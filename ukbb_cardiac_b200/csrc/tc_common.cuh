@@ -258,9 +258,14 @@ __device__ __forceinline__ float2 unpack16t(uint32_t u) {
 // lo = rn16(v - hi) (v - hi is exact in FP32).  FP16: hi is clamped to the finite range; inputs are >= 0 (post-ReLU) or small.
 template <bool F16>
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
-    hi = pack16t<F16>(a, b);
-    const float2 h = unpack16t<F16>(hi);
-    lo = pack16t<F16>(a - h.x, b - h.y);
+    if (F16) {
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - h.y), "f"(a - h.x));
+    } else {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - __uint_as_float(hi & 0xffff0000u)), "f"(a - __uint_as_float(hi << 16)));
+    }
 }
 __device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {
     if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
