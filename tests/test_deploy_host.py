@@ -163,3 +163,51 @@ def _gloo_worker(rank, world, root, rdzv):
     assert not set(gathered[0]) & set(gathered[1])
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_worker_devices_respect_callers_mask():
+    """--gpus N maps worker r through the caller's CUDA_VISIBLE_DEVICES instead of overwriting it (round-1 advisor finding)."""
+    assert deploy.worker_devices(3, env={}) == ["0", "1", "2"]
+    assert deploy.worker_devices(2, env={"CUDA_VISIBLE_DEVICES": "4,5,6,7"}) == ["4", "5"]
+    assert deploy.worker_devices(1, env={"CUDA_VISIBLE_DEVICES": " GPU-abc "}) == ["GPU-abc"]
+    with pytest.raises(SystemExit):
+        deploy.worker_devices(3, env={"CUDA_VISIBLE_DEVICES": "0,1"})
+
+
+def test_run_workers_drains_pipes_concurrently(monkeypatch, capsys):
+    """Every worker prints far more than a pipe holds (64 KB) before ANY of them may exit: with one reader per worker the run
+    finishes; draining the pipes one after the other in rank order would deadlock here (the round-1 behaviour serialised the GPUs)."""
+    import subprocess as sp
+    import sys
+    real_popen = sp.Popen
+    script = ("import sys, os, time\n"
+              "r = int(sys.argv[sys.argv.index('--shard_index') + 1])\n"
+              "d = os.environ['UKBB_TEST_RENDEZVOUS']\n"
+              "sys.stdout.write(('worker %d line\\n' % r) * 20000); sys.stdout.flush()\n"       # ~280 KB each
+              "open(os.path.join(d, 'done%d' % r), 'w').close()\n"
+              "t0 = time.time()\n"
+              "while not all(os.path.exists(os.path.join(d, 'done%d' % k)) for k in range(3)):\n"
+              "    assert time.time() - t0 < 60\n"
+              "    time.sleep(0.01)\n")
+
+    def fake_popen(cmd, **kw):
+        assert kw["env"]["CUDA_VISIBLE_DEVICES"] == cmd[cmd.index("--shard_index") + 1]
+        return real_popen([sys.executable, "-c", script] + cmd[3:], **kw)
+
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        monkeypatch.setenv("UKBB_TEST_RENDEZVOUS", d)
+        monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+        monkeypatch.setattr(deploy.subprocess, "Popen", fake_popen)
+        flags = deploy.parse_flags(["--gpus", "3"])
+        assert deploy.run_workers(flags, ["--gpus", "3"]) == 0
+    out = capsys.readouterr().out.splitlines()
+    assert len(out) == 60000
+    assert out[0] == "worker 0 line" and out[20000] == "worker 1 line" and out[-1] == "worker 2 line"     # replayed in rank order
+
+
+def test_default_mode_is_the_compliant_one():
+    assert deploy.parse_flags([]).mode == "fp16x3"
+    assert deploy.parse_flags(["--mode", "bf16"]).mode == "bf16"
+    with pytest.raises(SystemExit):
+        deploy.parse_flags(["--mode", "int8"])

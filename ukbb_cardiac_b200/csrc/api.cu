@@ -230,6 +230,7 @@ int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode
         cudaError_t e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_pre, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_ws, cudaEventDisableTiming);
         for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
             e = cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_compute[s], cudaEventDisableTiming);
@@ -263,6 +264,7 @@ void ukbb_fcn_destroy(ukbb_fcn* hh) {
         if (h->ev_pre[s]) cudaEventDestroy(h->ev_pre[s]);
         cudaFree(h->st_pad[s]);
     }
+    if (h->ev_ws) cudaEventDestroy(h->ev_ws);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->s_pre) cudaStreamDestroy(h->s_pre);
@@ -281,8 +283,13 @@ int ukbb_fcn_preprocess(ukbb_fcn* hh, float* vol, long long n_slices, int x, int
     UKBB_REQUIRE(h && vol && out, "preprocess: null argument");
     UKBB_REQUIRE(n_slices > 0 && x > 0 && y > 0, "preprocess: empty volume (%lld slices of %dx%d)", n_slices, x, y);
     UKBB_CUDA(cudaSetDevice(h->device));
-    return launch_preprocess(h->pre, vol, n_slices, x, y, q_lo, q_hi, x2, y2, x_pre, y_pre, out, vl_vh, clip_in_place,
-                             (cudaStream_t)stream, &h->launches);
+    // the handle owns ONE selection workspace (histograms, scan state, lookup table): order this call after its previous user,
+    // whichever stream that was (another caller stream, or the internal stream of ukbb_fcn_segment_host)
+    UKBB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_ws, 0));
+    const int rc = launch_preprocess(h->pre, vol, n_slices, x, y, q_lo, q_hi, x2, y2, x_pre, y_pre, out, vl_vh, clip_in_place,
+                                     (cudaStream_t)stream, &h->launches);
+    UKBB_CUDA(cudaEventRecord(h->ev_ws, (cudaStream_t)stream));
+    return rc;
 }
 
 int ukbb_fcn_class_counts(ukbb_fcn* hh, long long* counts, int n, void* stream) {
@@ -333,9 +340,11 @@ int ukbb_fcn_segment_host(ukbb_fcn* hh, const float* vol, int x, int y, int z, i
     UKBB_CUDA(cudaStreamWaitEvent(h->s_pre, h->ev_h2d[slot], 0));
     UKBB_CUDA(cudaStreamWaitEvent(h->s_pre, h->ev_compute[slot], 0));    // forward of this slot's previous occupant has read st_pad[slot]
     UKBB_CUDA(cudaStreamWaitEvent(h->s_pre, h->ev_d2h[slot], 0));        // ... and its (vl, vh) have been read back
+    UKBB_CUDA(cudaStreamWaitEvent(h->s_pre, h->ev_ws, 0));               // a public ukbb_fcn_preprocess call may be using the workspace
     int rc = launch_preprocess(h->pre, h->st_vol[slot], n, x, y, q_lo, q_hi, x2, y2, x_pre, y_pre, h->st_pad[slot],
                                h->st_vlvh[slot], 0, h->s_pre, &h->launches);
     if (rc) return rc;
+    UKBB_CUDA(cudaEventRecord(h->ev_ws, h->s_pre));
     UKBB_CUDA(cudaEventRecord(h->ev_pre[slot], h->s_pre));
     UKBB_CUDA(cudaStreamWaitEvent(st, h->ev_pre[slot], 0));
     UKBB_CUDA(cudaStreamWaitEvent(st, h->ev_d2h[slot], 0));      // label staging of this slot drained

@@ -39,6 +39,7 @@ struct Engine {
     size_t st_pad_cap[2] = {0, 0};
     // preprocessing of subject s + 1 (own stream) overlaps the forward of subject s (caller's stream)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_pre = nullptr;
+    cudaEvent_t ev_ws = nullptr;                          // last use of the (single) selection workspace `pre`, on whichever stream
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_pre[2] = {nullptr, nullptr};
 };
 

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import threading
 from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
@@ -76,6 +77,8 @@ class FCNEngine:
         _lib.check(self.lib.ukbb_fcn_create(C.byref(fw), self.n_class, device, MODES[mode], C.byref(handle)))
         self._h = handle
         self._slot = 0
+        self._pin_pool, self._pin_live, self._pin_lock = [], {}, threading.Lock()
+        self._join_stream = None
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -174,6 +177,80 @@ class FCNEngine:
 
     def sync(self) -> None:
         _lib.check(self.lib.ukbb_fcn_sync(self._h))
+
+    # ---- pipelined whole-volume calls (deploy.py): decode of subject i + 1, device work of subject i and encode of subject i - 1 overlap
+    def host_buffer(self, nbytes: int) -> np.ndarray:
+        """A uint8 numpy view of pinned host memory from a small reuse pool (cudaHostAlloc is slow: ~10 ms per 80 MB).
+        Thread-safe: deploy.py's reader threads decode into these buffers."""
+        with self._pin_lock:
+            best = -1
+            for i, t in enumerate(self._pin_pool):
+                if t.numel() >= nbytes and (best < 0 or t.numel() < self._pin_pool[best].numel()):
+                    best = i
+            buf = self._pin_pool.pop(best) if best >= 0 else None
+        if buf is None:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        arr = buf.numpy()
+        with self._pin_lock:
+            self._pin_live[arr.ctypes.data] = buf
+        return arr
+
+    def release_host_buffer(self, arr: np.ndarray) -> None:
+        """Give a `host_buffer` array (the array itself, not a view of it) back to the pool."""
+        with self._pin_lock:
+            t = self._pin_live.pop(arr.ctypes.data, None)
+            if t is not None:
+                self._pin_pool.append(t)
+
+    def submit_volume(self, image: np.ndarray, q: Sequence[float] = (1.0, 99.0)):
+        """Asynchronous `segment_volume`: image (X, Y[, Z[, T]]) float32; when it is a Fortran-ordered view of a `host_buffer` it is
+        uploaded from where it lies.  Returns a ticket for `collect_volume`."""
+        shp = tuple(image.shape)
+        x, y = shp[0], shp[1]
+        z = shp[2] if image.ndim >= 3 else 1
+        t = shp[3] if image.ndim == 4 else 1
+        if image.ndim not in (2, 3, 4):
+            raise ValueError("expected a 2-D, 3-D or 4-D image, got shape %s" % (shp,))
+        n = x * y * z * t
+        own = None
+        if image.dtype == np.float32 and image.flags.f_contiguous:
+            flat = image.reshape(-1, order="F")                       # a view: NIfTI memory order = Fortran order
+        else:
+            own = self.host_buffer(n * 4)
+            flat = own[:n * 4].view(np.float32)
+            flat[:] = np.asarray(image, dtype=np.float32).reshape(-1, order="F")
+        lab_buf = self.host_buffer(n)
+        aux = self.host_buffer(16 + z * t * self.n_class * 8)
+        vol_t = torch.from_numpy(flat)
+        lab_t = torch.from_numpy(lab_buf[:n])
+        vlvh_t = torch.from_numpy(aux[:16].view(np.float64))
+        counts_t = torch.from_numpy(aux[16:16 + z * t * self.n_class * 8].view(np.int64))
+        self.segment_host_async(vol_t, (x, y, z, t), lab_t, vlvh_t, counts_t, q)
+        if self._join_stream is None:
+            self._join_stream = torch.cuda.Stream(self.device)
+        side = self._join_stream
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(side):                                 # the read-back is awaited on a side stream: the next forward is not held up
+            self.join()
+            ev.record(side)
+        return {"ev": ev, "shape": shp, "n": n, "zt": (z, t), "lab": lab_buf, "aux": aux, "own": own, "keep": (vol_t, lab_t, vlvh_t, counts_t)}
+
+    def collect_volume(self, ticket):
+        """Wait for a `submit_volume` ticket: (labels uint8 view of pinned memory, Fortran order, (vl, vh), counts int64 [T, Z, C]).
+        The labels stay valid until `release_ticket`."""
+        ticket["ev"].synchronize()
+        n, (z, t) = ticket["n"], ticket["zt"]
+        lab = ticket["lab"][:n].reshape(ticket["shape"], order="F")
+        vlvh = ticket["aux"][:16].view(np.float64)
+        counts = ticket["aux"][16:16 + z * t * self.n_class * 8].view(np.int64).reshape(t, z, self.n_class).copy()
+        return lab, (float(vlvh[0]), float(vlvh[1])), counts
+
+    def release_ticket(self, ticket) -> None:
+        for k in ("lab", "aux", "own"):
+            if ticket.get(k) is not None:
+                self.release_host_buffer(ticket[k])
+                ticket[k] = None
+        ticket["keep"] = None
 
     def segment_volume(self, image: np.ndarray, q: Sequence[float] = (1.0, 99.0)):
         """image: (X, Y, Z, T), (X, Y, Z) or (X, Y) array as returned by ``nim.get_data()``.

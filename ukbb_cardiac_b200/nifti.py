@@ -11,6 +11,7 @@ image gets sform_code=2 / qform_code=0, scl_slope/inter applied on read when val
 from __future__ import annotations
 
 import gzip
+import zlib
 import io
 import os
 from typing import Optional, Tuple
@@ -170,14 +171,8 @@ class Nifti1Image:
     get_fdata = get_data
 
 
-def load(path: str) -> Nifti1Image:
-    with open(path, "rb") as f:
-        raw = f.read()
-    if raw[:2] == b"\x1f\x8b":
-        raw = gzip.decompress(raw)
-    if len(raw) < 352:
-        raise ValueError("%s: too small for a NIfTI-1 file" % path)
-    hdr = np.frombuffer(raw[:348], dtype=_HDR)[0].copy()
+def _parse_header(raw348: bytes, path: str):
+    hdr = np.frombuffer(raw348, dtype=_HDR)[0].copy()
     if int(hdr["sizeof_hdr"]) != 348:
         raise ValueError("%s: not a little-endian NIfTI-1 file (sizeof_hdr=%d)" % (path, int(hdr["sizeof_hdr"])))
     if bytes(hdr["magic"])[:3] != b"n+1":
@@ -191,11 +186,107 @@ def load(path: str) -> Nifti1Image:
         raise TypeError("%s: unsupported NIfTI datatype code %d" % (path, code))
     dt = np.dtype(_CODE2DT[code]).newbyteorder("<")
     off = int(hdr["vox_offset"]) or 352
+    return hdr, shape, dt, off
+
+
+def _member_index(raw: bytes):
+    """Members of a .gz file written by `gzip_parallel`: every member header carries an extra subfield ('U', 'K') with the
+    compressed size of the member and the size of its payload (the BGZF idea), so the members can be located without
+    inflating and inflated independently.  Returns [(deflate offset, deflate length, payload offset, payload length)] or None
+    when the file was written by something else (then it is one sequential stream)."""
+    pos, out_pos, idx = 0, 0, []
+    n = len(raw)
+    while pos < n:
+        if n - pos < 28 or raw[pos:pos + 4] != b"\x1f\x8b\x08\x04":
+            return None
+        xlen = int.from_bytes(raw[pos + 10:pos + 12], "little")
+        if xlen != 12 or raw[pos + 12:pos + 14] != b"UK" or raw[pos + 14:pos + 16] != b"\x08\x00":
+            return None
+        msize = int.from_bytes(raw[pos + 16:pos + 20], "little")
+        psize = int.from_bytes(raw[pos + 20:pos + 24], "little")
+        if msize < 32 or pos + msize > n:
+            return None
+        idx.append((pos + 24, msize - 32, out_pos, psize))
+        pos += msize
+        out_pos += psize
+    return idx
+
+
+def _inflate_member(args):
+    raw, off, ln, dst, out_off, psize = args
+    chunk = zlib.decompress(raw[off:off + ln], -15)
+    if len(chunk) != psize:
+        raise ValueError("corrupt gzip member: %d bytes inflated, index says %d" % (len(chunk), psize))
+    if (zlib.crc32(chunk) & 0xffffffff) != int.from_bytes(raw[off + ln:off + ln + 4], "little"):
+        raise ValueError("corrupt gzip member: CRC mismatch")
+    dst[out_off:out_off + psize] = np.frombuffer(chunk, dtype=np.uint8)
+
+
+def read_decompressed(path: str, alloc=None, threads: Optional[int] = None):
+    """The decompressed bytes of a .nii / .nii.gz file as a uint8 array.  `alloc(nbytes)` may supply the destination (e.g. a view
+    of pinned host memory).  Files written by `save` (indexed multi-member gzip) are inflated member-parallel on a thread pool
+    (zlib releases the GIL) straight into the destination; any other .gz is one sequential stream and is inflated in pieces
+    into the destination, so callers get their parallelism from decoding several files at once."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    alloc = alloc or (lambda nbytes: np.empty(nbytes, dtype=np.uint8))
+    if raw[:2] != b"\x1f\x8b":
+        dst = alloc(len(raw))
+        dst[:len(raw)] = np.frombuffer(raw, dtype=np.uint8)
+        return dst[:len(raw)]
+    idx = _member_index(raw)
+    if idx is not None:
+        total = idx[-1][2] + idx[-1][3]
+        dst = alloc(total)
+        jobs = [(raw, off, ln, dst, out_off, psize) for off, ln, out_off, psize in idx]
+        if len(jobs) == 1:
+            _inflate_member(jobs[0])
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=threads or min(8, os.cpu_count() or 1)) as pool:
+                list(pool.map(_inflate_member, jobs))
+        return dst[:total]
+    # foreign writer (nibabel, dcm2niix, ...): sequential stream(s), inflated in 8 MB pieces
+    pieces, produced = [], 0
+    d, data = zlib.decompressobj(31), memoryview(raw)
+    while True:
+        piece = d.decompress(data, 8 << 20)
+        if piece:
+            pieces.append(piece)
+            produced += len(piece)
+        if d.unconsumed_tail:
+            data = d.unconsumed_tail
+            continue
+        if d.eof and d.unused_data:                                     # next member of a plain multi-member stream
+            data, d = d.unused_data, zlib.decompressobj(31)
+            continue
+        if not d.eof and not piece:
+            raise ValueError("%s: truncated gzip stream" % path)
+        if d.eof:
+            break
+        data = b""
+    dst = alloc(produced)
+    o = 0
+    for piece in pieces:
+        dst[o:o + len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+        o += len(piece)
+    return dst[:produced]
+
+
+def load(path: str, alloc=None) -> Nifti1Image:
+    """Read a NIfTI-1 file.  With `alloc`, the decompressed file lands in caller-provided memory and the image data is a VIEW of
+    it whenever the on-disk dtype is native little-endian (no copy: UK Biobank volumes are float32, data/biobank_utils.py:314)."""
+    raw = read_decompressed(path, alloc)
+    if len(raw) < 352:
+        raise ValueError("%s: too small for a NIfTI-1 file" % path)
+    hdr, shape, dt, off = _parse_header(raw[:348].tobytes(), path)
     n = int(np.prod(shape))
     if len(raw) < off + n * dt.itemsize:
         raise ValueError("%s: truncated voxel data" % path)
-    data = np.frombuffer(raw, dtype=dt, count=n, offset=off).astype(dt.newbyteorder("=")).reshape(shape, order="F")
-    return Nifti1Image(data, None, hdr)
+    data = np.frombuffer(raw, dtype=dt, count=n, offset=off)
+    if dt.newbyteorder("=") != dt or alloc is None:
+        data = data.astype(dt.newbyteorder("="))
+    return Nifti1Image(data.reshape(shape, order="F"), None, hdr)
 
 
 _PAR_CHUNK = 8 << 20          # bytes of payload per gzip member when compressing in parallel
@@ -203,8 +294,14 @@ _PAR_MIN = 32 << 20           # smaller payloads are written as one member
 
 
 def _gzip_member(args) -> bytes:
+    """One gzip member (RFC 1952) with an extra subfield 'UK' = (member size, payload size), see `_member_index`."""
     chunk, level = args
-    return gzip.compress(chunk, compresslevel=level, mtime=0)
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    body = c.compress(chunk) + c.flush()
+    msize = 24 + len(body) + 8
+    head = (b"\x1f\x8b\x08\x04" + b"\x00\x00\x00\x00" + (b"\x04" if level == 1 else b"\x00") + b"\xff" + b"\x0c\x00" + b"UK" + b"\x08\x00" +
+            msize.to_bytes(4, "little") + len(chunk).to_bytes(4, "little"))
+    return head + body + (zlib.crc32(chunk) & 0xffffffff).to_bytes(4, "little") + (len(chunk) & 0xffffffff).to_bytes(4, "little")
 
 
 def gzip_parallel(payload, compresslevel: int = 1, threads: Optional[int] = None) -> bytes:
@@ -212,9 +309,9 @@ def gzip_parallel(payload, compresslevel: int = 1, threads: Optional[int] = None
     A multi-member stream is a valid .gz file (RFC 1952 section 2.2): `gzip.decompress`, `gzip.open`, zlib's gzread -- hence
     nibabel -- return the concatenation.  The reference writes a float64 label volume per sequence (160 MB for one SA
     subject, deploy_network.py:134-137), whose single-threaded deflate dominates the wall clock of the drop-in CLI."""
-    view = memoryview(payload)
+    view = memoryview(payload).cast("B")
     if len(view) < _PAR_MIN:
-        return gzip.compress(view, compresslevel=compresslevel, mtime=0)
+        return _gzip_member((view, compresslevel))
     from concurrent.futures import ThreadPoolExecutor
     n_thr = threads or min(16, os.cpu_count() or 1)
     chunks = [(view[o:o + _PAR_CHUNK], compresslevel) for o in range(0, len(view), _PAR_CHUNK)]
