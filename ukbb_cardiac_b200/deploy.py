@@ -202,7 +202,7 @@ def deploy(flags: Flags, engine=None, out=sys.stdout, stage_times: Optional[Dict
             todo.append((data, data_dir, image_name, skip))
         n_readers = max(1, min(4, (os.cpu_count() or 2) // 2))
         readers = ThreadPoolExecutor(max_workers=n_readers)
-        writers = ThreadPoolExecutor(max_workers=2)
+        writers = ThreadPoolExecutor(max_workers=3)
         LOOKAHEAD = n_readers + 1
 
         def read_job(path):
@@ -224,16 +224,16 @@ def deploy(flags: Flags, engine=None, out=sys.stdout, stage_times: Optional[Dict
         def write_job(data_dir, nim, image, bufs, ticket, labels, vl, vh, k):
             t0 = time.time()
             try:
-                pred = labels.astype(label_dt, order="F")
-                nim2 = nifti.Nifti1Image(pred, nim.affine)
+                # uint8 labels are widened to the reference's float64 volume (:92) chunk by chunk inside the gzip workers
+                nim2 = nifti.Nifti1Image(labels, nim.affine)
                 nim2.header["pixdim"] = nim.header["pixdim"]           # :137
-                nifti.save(nim2, "{0}/{1}_{2}.nii.gz".format(data_dir, prefix, flags.seq_name))
+                nifti.save(nim2, "{0}/{1}_{2}.nii.gz".format(data_dir, prefix, flags.seq_name), dtype=label_dt, label_data=True)
                 for fr in ("ED", "ES"):
                     frame = clip_like_reference(image[:, :, :, k[fr]], vl, vh)
                     nifti.save(nifti.Nifti1Image(np.asfortranarray(frame), nim.affine),
                                "{0}/{1}_{2}.nii.gz".format(data_dir, flags.seq_name, fr))   # :144-146
-                    nifti.save(nifti.Nifti1Image(np.asfortranarray(pred[:, :, :, k[fr]]), nim.affine),
-                               "{0}/{1}_{2}_{3}.nii.gz".format(data_dir, prefix, flags.seq_name, fr))   # :147-151
+                    nifti.save(nifti.Nifti1Image(np.asfortranarray(labels[:, :, :, k[fr]]), nim.affine),
+                               "{0}/{1}_{2}_{3}.nii.gz".format(data_dir, prefix, flags.seq_name, fr), dtype=label_dt, label_data=True)   # :147-151
             finally:
                 eng.release_ticket(ticket)
                 for b_ in bufs:

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import gzip
 import zlib
+import threading
 import io
 import os
 from typing import Optional, Tuple
@@ -242,9 +243,7 @@ def read_decompressed(path: str, alloc=None, threads: Optional[int] = None):
         if len(jobs) == 1:
             _inflate_member(jobs[0])
         else:
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(max_workers=threads or min(8, os.cpu_count() or 1)) as pool:
-                list(pool.map(_inflate_member, jobs))
+            list(_pool().map(_inflate_member, jobs))
         return dst[:total]
     # foreign writer (nibabel, dcm2niix, ...): sequential stream(s), inflated in 8 MB pieces
     pieces, produced = [], 0
@@ -291,17 +290,37 @@ def load(path: str, alloc=None) -> Nifti1Image:
 
 _PAR_CHUNK = 8 << 20          # bytes of payload per gzip member when compressing in parallel
 _PAR_MIN = 32 << 20           # smaller payloads are written as one member
+_POOL = None
+_POOL_LOCK = threading.Lock()
+
+
+def _pool():
+    """One process-wide thread pool for gzip members (deflate and inflate release the GIL); its workers never submit work
+    themselves, so readers / writers of several files may share it."""
+    global _POOL
+    with _POOL_LOCK:
+        if _POOL is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _POOL = ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 2), thread_name_prefix="ukbb-gz")
+        return _POOL
 
 
 def _gzip_member(args) -> bytes:
-    """One gzip member (RFC 1952) with an extra subfield 'UK' = (member size, payload size), see `_member_index`."""
-    chunk, level = args
-    c = zlib.compressobj(level, zlib.DEFLATED, -15)
-    body = c.compress(chunk) + c.flush()
+    """One gzip member (RFC 1952) with an extra subfield 'UK' = (member size, payload size), see `_member_index`.
+    args = (prefix bytes, source (bytes-like, or an array slice converted to `dtype` here, in the worker), dtype, level)."""
+    prefix, src, dtype, level = args[:4]
+    strategy = args[4] if len(args) > 4 else zlib.Z_DEFAULT_STRATEGY
+    if dtype is not None:
+        src = np.ascontiguousarray(src, dtype=dtype)
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+    body = (c.compress(prefix) if prefix else b"") + c.compress(src) + c.flush()
+    view = memoryview(src).cast("B")
+    plen = len(prefix) + len(view)
+    crc = zlib.crc32(view, zlib.crc32(prefix)) & 0xffffffff
     msize = 24 + len(body) + 8
     head = (b"\x1f\x8b\x08\x04" + b"\x00\x00\x00\x00" + (b"\x04" if level == 1 else b"\x00") + b"\xff" + b"\x0c\x00" + b"UK" + b"\x08\x00" +
-            msize.to_bytes(4, "little") + len(chunk).to_bytes(4, "little"))
-    return head + body + (zlib.crc32(chunk) & 0xffffffff).to_bytes(4, "little") + (len(chunk) & 0xffffffff).to_bytes(4, "little")
+            msize.to_bytes(4, "little") + plen.to_bytes(4, "little"))
+    return head + body + crc.to_bytes(4, "little") + (plen & 0xffffffff).to_bytes(4, "little")
 
 
 def gzip_parallel(payload, compresslevel: int = 1, threads: Optional[int] = None) -> bytes:
@@ -311,22 +330,40 @@ def gzip_parallel(payload, compresslevel: int = 1, threads: Optional[int] = None
     subject, deploy_network.py:134-137), whose single-threaded deflate dominates the wall clock of the drop-in CLI."""
     view = memoryview(payload).cast("B")
     if len(view) < _PAR_MIN:
-        return _gzip_member((view, compresslevel))
-    from concurrent.futures import ThreadPoolExecutor
-    n_thr = threads or min(16, os.cpu_count() or 1)
-    chunks = [(view[o:o + _PAR_CHUNK], compresslevel) for o in range(0, len(view), _PAR_CHUNK)]
-    with ThreadPoolExecutor(max_workers=n_thr) as pool:
-        return b"".join(pool.map(_gzip_member, chunks))
+        return _gzip_member((b"", view, None, compresslevel))
+    chunks = [(b"", view[o:o + _PAR_CHUNK], None, compresslevel) for o in range(0, len(view), _PAR_CHUNK)]
+    return b"".join(_pool().map(_gzip_member, chunks))
 
 
-def save(img: Nifti1Image, path: str, compresslevel: int = 1) -> None:
+def save(img: Nifti1Image, path: str, compresslevel: int = 1, dtype=None, label_data: bool = False) -> None:
+    """Write a single-file NIfTI-1 image.  `dtype` stores the data converted to another type (e.g. uint8 label maps as the
+    reference's float64 volumes, deploy_network.py:92,134-137): the conversion happens chunk by chunk inside the gzip workers,
+    so the 8x larger array never exists in memory.  `label_data` selects zlib's run-length strategy, which deflates label
+    volumes (long runs of identical values) about twice as fast as the default strategy and slightly smaller."""
+    strategy = zlib.Z_RLE if label_data else zlib.Z_DEFAULT_STRATEGY
     img._sync_shape()
     h = img.header.copy()
+    data = np.asarray(img._data)
+    out_dt = np.dtype(dtype if dtype is not None else data.dtype).newbyteorder("=")
+    if out_dt not in _DT2CODE:
+        raise TypeError("dtype %s cannot be stored in NIfTI-1 by this writer" % out_dt)
+    h["datatype"] = _DT2CODE[out_dt]
+    h["bitpix"] = out_dt.itemsize * 8
     h["vox_offset"] = 352.0
     h["magic"] = b"n+1"
-    payload = h.tobytes() + b"\x00\x00\x00\x00" + np.asarray(img._data).astype(
-        np.dtype(img._data.dtype).newbyteorder("<")).tobytes(order="F")
-    tmp = path + ".tmp%d" % os.getpid()
+    head = h.tobytes() + b"\x00\x00\x00\x00"
+    flat = data.reshape(-1, order="F")                 # a view for Fortran-ordered data (NIfTI order), else one copy
+    le = out_dt.newbyteorder("<")
+    tmp = path + ".tmp%d_%d" % (os.getpid(), threading.get_ident())
     with open(tmp, "wb") as f:
-        f.write(gzip_parallel(payload, compresslevel) if path.endswith(".gz") else payload)
+        if not path.endswith(".gz"):
+            f.write(head)
+            f.write(np.ascontiguousarray(flat, dtype=le).tobytes())
+        elif flat.size * out_dt.itemsize < _PAR_MIN:
+            f.write(_gzip_member((head, flat, le, compresslevel, strategy)))
+        else:
+            step = _PAR_CHUNK // out_dt.itemsize
+            jobs = [(head if o == 0 else b"", flat[o:o + step], le, compresslevel, strategy) for o in range(0, flat.size, step)]
+            for member in _pool().map(_gzip_member, jobs):
+                f.write(member)
     os.replace(tmp, path)
