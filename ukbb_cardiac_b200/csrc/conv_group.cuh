@@ -39,7 +39,11 @@ struct ConvGroupParams {
     int ho, wog;
 };
 
-// SPLIT: operands are hi + lo pairs of 16-bit values and every K-slice is three UMMAs (hi.hi + lo.hi + hi.lo, conv_tc.cu).
+// SPLIT: operands are hi + lo pairs of 16-bit values and every K-slice needs three products (hi.hi + lo.hi + hi.lo, tc_conv.cu).
+// An N = 64 UMMA from shared memory is bound by the operand port (4 KB of A + 2 KB of B = 48 cycles for 32 cycles of tensor work), so
+// the two products that share A_hi are ONE UMMA with N = 128: the weight tile of a K-slice is stored as [w_hi rows | w_lo rows] and
+// A_hi . [w_hi ; w_lo]^T lands in accumulator columns [0, 64) and [64, 128) (4 + 4 KB = 64 cycles instead of 2 x 48); A_lo . w_hi^T
+// adds into columns [0, 64).  The epilogue sums the two column blocks.  112 instead of 144 port cycles per K-slice.
 // TROWS: output rows per tile (<= 16; the UMMA still has M = 128 = 16 rows x 8 groups, rows >= TROWS are idle): the 64 -> 64 split
 // instance holds 144 KB of weights and fits two (hi, lo) patch stages only with 14-row tiles.
 template <int CC, int COUT, int STRIDE, bool SPLIT = false>
@@ -64,7 +68,8 @@ struct ConvGroupCfg {
     static constexpr int A_MAX = ((SPLIT ? 224 : 200) * 1024 - B_BYTES - 2 * OUT_BYTES) / A_STAGE_BYTES;
     static constexpr int A_STAGES = A_MAX > 4 ? 4 : A_MAX;
     static constexpr int ACC_STAGES = 2;
-    static constexpr int TMEM_COLS = 128;
+    static constexpr int ACC_COLS = SPLIT ? 2 * N : N;         // SPLIT: columns [0, N) = hi.hi + lo.hi, [N, 2N) = hi.lo
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_BYTES + 2 * OUT_BYTES + 1024 + 256 + 2 * N * 4;
     static_assert(N == 64, "pixel-group kernel is built for N = Gout * Cout = 64");
     static_assert(STRIDE == 1 || G >= 2, "stride 2 needs at least two pixels per row");
@@ -193,7 +198,11 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(wfull, (SPLIT ? 2 : 1) * Cfg::NB_TILES * N * Cfg::B_ROW);
-            for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) tma_load_2d(b_base + t * Cfg::B_TILE, &map_b, wfull, 0, t * N);   // hi tiles, then lo tiles
+            for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) {
+                // global: hi tiles, then lo tiles.  Shared (SPLIT): tile t = [hi 64 rows | lo 64 rows], one N = 128 B operand
+                const int tt = t % Cfg::NB_TILES, pl = t / Cfg::NB_TILES;
+                tma_load_2d(b_base + (SPLIT ? tt * 2 * Cfg::B_TILE + pl * Cfg::B_TILE : t * Cfg::B_TILE), &map_b, wfull, 0, t * N);
+            }
             griddep_wait();
             TileWalk w;
             w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
@@ -214,6 +223,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
         const bool leader = elect_one();
         const uint32_t idesc = F16 ? make_idesc_f16(128, N) : make_idesc_bf16(128, N);
+        const uint32_t idesc2 = F16 ? make_idesc_f16(128, 2 * N) : make_idesc_bf16(128, 2 * N);       // SPLIT: A_hi . [w_hi ; w_lo]^T
         constexpr uint32_t blayout = Cfg::B_ROW == 128 ? 2u : Cfg::B_ROW == 64 ? 4u : 6u;
         constexpr uint32_t a_hi = (uint32_t)(((STRIDE == 1 ? PU : 2 * PU) * 128) >> 4) | (1u << 14) | (2u << 29);
         constexpr uint32_t b_hi = (uint32_t)((8 * Cfg::B_ROW) >> 4) | (1u << 14) | (blayout << 29);
@@ -226,7 +236,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_wait(tempty(acc), acc_ph ^ 1);
             mbar_wait(a_full(as), aph);
             tc_fence_after();
-            const uint32_t d = tmem_base + acc * N;
+            const uint32_t d = tmem_base + acc * Cfg::ACC_COLS;
             const uint32_t a_lo = (((smem_base + as * Cfg::A_STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
             if (leader) {
 #pragma unroll
@@ -241,11 +251,12 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
                             const uint32_t ao = (uint32_t)((arow * 128 + sub * CC * 2 + ks * 32) >> 4);
-                            const uint32_t bo = (uint32_t)(((ky * J + j) * Cfg::B_TILE + ks * 32) >> 4);
-                            umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (ky | j | ks) != 0 ? 1u : 0u);
+                            const uint32_t bo = (uint32_t)(((ky * J + j) * (SPLIT ? 2 : 1) * Cfg::B_TILE + ks * 32) >> 4);
                             if (SPLIT) {
+                                umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc2, (ky | j | ks) != 0 ? 1u : 0u);           // hi . [hi ; lo]
                                 umma_bf16_lohi(d, a_lo + (Cfg::PATCH_BYTES >> 4) + ao, a_hi, b_lo + bo, b_hi, idesc, 1u);            // lo . hi
-                                umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + (Cfg::B_SET >> 4) + bo, b_hi, idesc, 1u);                  // hi . lo
+                            } else {
+                                umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (ky | j | ks) != 0 ? 1u : 0u);
                             }
                         }
                     }
@@ -268,7 +279,39 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int i = 0; i < my_tiles; ++i) {
             mbar_wait(tfull(acc), acc_ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
+            if (SPLIT) {
+                // acc = columns [0, 64) + columns [64, 128); hi / lo pieces, 128 contiguous bytes each per thread (this row's group),
+                // four 256-bit stores per plane
+                const int row = r >> 3, y = w.ty * TROWS + row, gx = w.tx * 8 + (r & 7);
+                const bool live = row < TROWS && y < p.ho && gx < p.wog;
+                uint32_t* dst = p.out + (((size_t)w.n * p.ho + y) * p.wog + gx) * 32;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t v[16], v2[16], oh[8], ol[8];
+                    tmem_ld16(taddr + 16 * c8, v);
+                    tmem_ld16(taddr + 64 + 16 * c8, v2);
+                    tmem_ld_wait();
+                    if (c8 == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty(acc));     // accumulator is in registers: release it to the MMA warp
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+#pragma unroll
+                    for (int c = 0; c < 16; c += 4) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
+                        bn_relu_split<F16>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
+                        bn_relu_split<F16>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1], ol[c / 2 + 1]);
+                    }
+                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
+                }
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                w.next();
+                continue;
+            }
             uint32_t v[64];
             tmem_ld32(taddr, v);
             tmem_ld32(taddr + 32, v + 32);
@@ -277,27 +320,6 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));         // accumulator is in registers: release it to the MMA warp
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
-            if (SPLIT) {
-                // hi / lo pieces, 128 contiguous bytes each per thread (this row's group), four 256-bit stores per plane
-                const int row = r >> 3, y = w.ty * TROWS + row, gx = w.tx * 8 + (r & 7);
-                const bool live = row < TROWS && y < p.ho && gx < p.wog;
-                uint32_t* dst = p.out + (((size_t)w.n * p.ho + y) * p.wog + gx) * 32;
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    uint32_t oh[8], ol[8];
-#pragma unroll
-                    for (int c = 0; c < 16; c += 4) {
-                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
-                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
-                        bn_relu_split<F16>(v[16 * c8 + c], v[16 * c8 + c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
-                        bn_relu_split<F16>(v[16 * c8 + c + 2], v[16 * c8 + c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1],
-                                           ol[c / 2 + 1]);
-                    }
-                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
-                }
-                w.next();
-                continue;
-            }
             uint32_t o[32];
 #pragma unroll
             for (int c = 0; c < 64; c += 4) {
