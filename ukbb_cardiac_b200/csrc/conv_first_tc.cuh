@@ -73,7 +73,13 @@ struct ConvFirstTcCfg {
     static constexpr int IMG_STAGES = 4;
     static constexpr int THREADS = 512;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int COL_ACC = 0, COL_D0 = 128, COL_A0 = 384;
+    // TMEM columns.  plain: conv0_1 accumulators 2 x 64 | D0 2 stages x 2 blocks x 64 | A0 2 stages x 2 blocks x 32.
+    // SPLIT: conv0_1 accumulators 2 x 128 (columns [0, 64) = hi.hi + lo.hi, [64, 128) = hi.lo: the N = 128 merge of conv_group.cuh) |
+    //        D0 ONE stage x 2 blocks x 64 (the finisher loads all 64 columns and releases it before converting) | A0 as before.
+    static constexpr int ACC_COLS = SPLIT ? 128 : 64;
+    static constexpr int D0_STAGES = SPLIT ? 1 : 2;
+    static constexpr int COL_ACC = 0, COL_D0 = 2 * ACC_COLS, COL_A0 = 384;
+    static_assert(COL_D0 + D0_STAGES * 2 * 64 <= COL_A0, "TMEM budget");
     static constexpr int SMEM_BYTES = A_STAGES * PATCH_BYTES + B_BYTES + B0_BYTES + 2 * OUT_BYTES + IMG_STAGES * IMG_BYTES + 256 /*barriers*/ +
                                       2 * N * 4 + 1024 /*align*/;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -139,7 +145,11 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
         // ===================== TMA producer: weights once, one FP32 image box per tile =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(wfull, (SPLIT ? 2 : 1) * Cfg::NB_TILES * Cfg::B_TILE + Cfg::B0_BYTES);
-            for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) tma_load_2d(b_base + t * Cfg::B_TILE, &map_b, wfull, 0, t * N);   // hi tiles, then lo tiles
+            for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) {
+                // global: hi tiles, then lo tiles.  Shared (SPLIT): tile t = [hi 64 rows | lo 64 rows], one N = 128 B operand
+                const int tt = t % Cfg::NB_TILES, pl = t / Cfg::NB_TILES;
+                tma_load_2d(b_base + (SPLIT ? tt * 2 * Cfg::B_TILE + pl * Cfg::B_TILE : t * Cfg::B_TILE), &map_b, wfull, 0, t * N);
+            }
             tma_load_2d(b0_base, &map_b0, wfull, 0, 0);
             griddep_wait();
             TileWalk w;
@@ -158,6 +168,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
         // ===================== MMA issuer (conv0_1, as conv_group<16, 16, 1>) =====================
         const bool leader = elect_one();
         const uint32_t idesc = F16 ? make_idesc_f16(128, N) : make_idesc_bf16(128, N);
+        const uint32_t idesc2 = F16 ? make_idesc_f16(128, 2 * N) : make_idesc_bf16(128, 2 * N);    // SPLIT: A_hi . [w_hi ; w_lo]^T
         constexpr uint32_t a_hi = (uint32_t)((PU * 128) >> 4) | (1u << 14) | (2u << 29);       // 8-row groups one patch row apart, 128 B swizzle
         constexpr uint32_t b_hi = (uint32_t)((8 * 32) >> 4) | (1u << 14) | (6u << 29);         // weights: 32-byte rows, 32 B swizzle
         const uint32_t b_lo = ((b_base & 0x3FFFF) >> 4) | (1u << 16);
@@ -169,7 +180,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             mbar_wait(tempty(acc), acc_ph ^ 1);
             mbar_wait(a_full(as), aph);
             tc_fence_after();
-            const uint32_t d = tmem_base + Cfg::COL_ACC + acc * N;
+            const uint32_t d = tmem_base + Cfg::COL_ACC + acc * Cfg::ACC_COLS;
             const uint32_t a_lo = (((smem_base + as * Cfg::PATCH_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
             if (leader) {
 #pragma unroll
@@ -180,11 +191,12 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                         const int ro = jj < 0 ? -1 : jj / 4;
                         const int sub = jj - ro * 4;
                         const int arow = ky * PU + 1 + ro;
-                        const uint32_t ao = (uint32_t)((arow * 128 + sub * 32) >> 4), bo = (uint32_t)(((ky * J + j) * Cfg::B_TILE) >> 4);
-                        umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (ky | j) != 0 ? 1u : 0u);
+                        const uint32_t ao = (uint32_t)((arow * 128 + sub * 32) >> 4), bo = (uint32_t)(((ky * J + j) * (SPLIT ? 2 : 1) * Cfg::B_TILE) >> 4);
                         if (SPLIT) {
+                            umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc2, (ky | j) != 0 ? 1u : 0u);                    // hi . [hi ; lo]
                             umma_bf16_lohi(d, a_lo + (Cfg::PLANE_BYTES >> 4) + ao, a_hi, b_lo + bo, b_hi, idesc, 1u);                // lo . hi
-                            umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + (Cfg::B_SET >> 4) + bo, b_hi, idesc, 1u);                      // hi . lo
+                        } else {
+                            umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (ky | j) != 0 ? 1u : 0u);
                         }
                     }
                 umma_commit(a_empty(as));
@@ -205,7 +217,9 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
         for (int i = 0; i < my_tiles; ++i) {
             const int s = i & 1;
             const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-            mbar_wait(BAR(D0_EMPTY + s), ph ^ 1);
+            const int ds = SPLIT ? 0 : s;                                            // D0 stage (SPLIT: one stage, phase = tile parity)
+            const uint32_t dph = SPLIT ? ((uint32_t)i & 1u) : ph;
+            mbar_wait(BAR(D0_EMPTY + ds), dph ^ 1);
             mbar_wait(BAR(A0_FULL + s), ph);
             tc_fence_after();
             if (leader) {
@@ -213,10 +227,10 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                 for (int m = 0; m < 2; ++m)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_ts_lohi(tmem_base + Cfg::COL_D0 + (s * 2 + m) * 64, tmem_base + Cfg::COL_A0 + (s * 2 + m) * 32 + 8 * k, b_lo + 2 * k, b_hi,
+                        umma_ts_lohi(tmem_base + Cfg::COL_D0 + (ds * 2 + m) * 64, tmem_base + Cfg::COL_A0 + (s * 2 + m) * 32 + 8 * k, b_lo + 2 * k, b_hi,
                                      idesc, k != 0 ? 1u : 0u);
                 umma_commit(BAR(A0_EMPTY + s));
-                umma_commit(BAR(D0_FULL + s));
+                umma_commit(BAR(D0_FULL + ds));
             }
             __syncwarp();
         }
@@ -274,28 +288,33 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             if (i + 1 < my_tiles) build(i + 1);
             // ---- finish tile i: D0 -> shift + ReLU -> 16 bit -> the 128-byte patch row of conv0_1
             const int s = i & 1, as = i % AST;
-            mbar_wait(BAR(D0_FULL + s), ((uint32_t)i >> 1) & 1u);
-            tc_fence_after();
+            if (!SPLIT) {
+                mbar_wait(BAR(D0_FULL + s), ((uint32_t)i >> 1) & 1u);
+                tc_fence_after();
+            }
             // SAME padding of conv0_1 pads a0 with zeros: groups outside the image are zero, not conv0_0 of a zero image
             const int y = w.ty * 16 - 1 + py, gx = w.tx * 8 - 1 + pg;
             const bool inside = y >= 0 && y < p.h && gx >= 0 && gx < p.w4;
             if (SPLIT) {
-                // 16 accumulator columns (one pixel) at a time: hi and lo rows of the patch, two swizzled STS.128 each
+                // D0 has ONE stage here: load all 64 accumulator columns, release it, then convert (one pixel = 16 columns at a time)
+                // into the hi and lo rows of the patch, two swizzled STS.128 each
+                uint32_t d[64];
+                mbar_wait(BAR(D0_FULL), (uint32_t)i & 1u);
+                tc_fence_after();
+                tmem_ld32(lane_base + Cfg::COL_D0 + m * 64, d);
+                tmem_ld32(lane_base + Cfg::COL_D0 + m * 64 + 32, d + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(D0_EMPTY));
                 mbar_wait(a_empty(as), ((uint32_t)(i / AST) & 1u) ^ 1u);
                 const uint32_t row = smem_base + as * Cfg::PATCH_BYTES + (uint32_t)g * 128u;
 #pragma unroll
                 for (int qt = 0; qt < 4; ++qt) {
-                    uint32_t d[16], oh[8], ol[8];
-                    tmem_ld16(lane_base + Cfg::COL_D0 + (s * 2 + m) * 64 + 16 * qt, d);
-                    tmem_ld_wait();
-                    if (qt == 3) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR(D0_EMPTY + s));
-                    }
+                    uint32_t oh[8], ol[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        add_relu_split<F16>(d[2 * c], d[2 * c + 1], p.shift0[2 * c], p.shift0[2 * c + 1], oh[c], ol[c]);
+                        add_relu_split<F16>(d[16 * qt + 2 * c], d[16 * qt + 2 * c + 1], p.shift0[2 * c], p.shift0[2 * c + 1], oh[c], ol[c]);
                         if (!inside) { oh[c] = 0u; ol[c] = 0u; }
                     }
                     if (active) {
@@ -356,7 +375,37 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
         for (int i = 0; i < my_tiles; ++i) {
             mbar_wait(tfull(acc), acc_ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::COL_ACC + acc * N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::COL_ACC + acc * Cfg::ACC_COLS;
+            if (SPLIT) {
+                const int y = w.ty * 16 + (r >> 3), gx = w.tx * 8 + (r & 7);
+                const bool live = y < p.h && gx < p.w4;
+                uint32_t* dst = p.out + (((size_t)w.n * p.h + y) * p.w4 + gx) * 32;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t v[16], v2[16], oh[8], ol[8];
+                    tmem_ld16(taddr + 16 * c8, v);
+                    tmem_ld16(taddr + 64 + 16 * c8, v2);
+                    tmem_ld_wait();
+                    if (c8 == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty(acc));
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+#pragma unroll
+                    for (int c = 0; c < 16; c += 4) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
+                        bn_relu_split<F16>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
+                        bn_relu_split<F16>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1], ol[c / 2 + 1]);
+                    }
+                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
+                }
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                w.next();
+                continue;
+            }
             uint32_t v[64];
             tmem_ld32(taddr, v);
             tmem_ld32(taddr + 32, v + 32);
@@ -365,26 +414,6 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
-            if (SPLIT) {
-                const int y = w.ty * 16 + (r >> 3), gx = w.tx * 8 + (r & 7);
-                const bool live = y < p.h && gx < p.w4;
-                uint32_t* dst = p.out + (((size_t)w.n * p.h + y) * p.w4 + gx) * 32;
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    uint32_t oh[8], ol[8];
-#pragma unroll
-                    for (int c = 0; c < 16; c += 4) {
-                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
-                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
-                        bn_relu_split<F16>(v[16 * c8 + c], v[16 * c8 + c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
-                        bn_relu_split<F16>(v[16 * c8 + c + 2], v[16 * c8 + c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1],
-                                           ol[c / 2 + 1]);
-                    }
-                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
-                }
-                w.next();
-                continue;
-            }
             uint32_t o[32];
 #pragma unroll
             for (int c = 0; c < 64; c += 4) {
