@@ -112,7 +112,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (warp != 0) griddep_wait();                       // the producer waits after it has issued the weight loads
-    const int tiles_per_slice = p.tiles_x * p.tiles_y;
+    // Tile order: x-tile index slowest (tile = (tx * n + slice) * tiles_y + ty).  The two CTAs of a cluster walk the weight stream in
+    // lockstep on tiles 2c and 2c + 1; a border tile whose right sub-tile lies outside the image (24 columns = 1.5 tiles at level 3) has
+    // half the UMMAs, and with the x-tile index fastest every cluster paired a full tile with a half tile (rank 1 idled a quarter of the
+    // time).  Now the pair almost always holds two tiles of the same kind.
+    const int tiles_per_tx = p.tiles_y * p.n;
     // tile walk: plain round-robin, or (CL) pairs of tiles dealt to clusters; the odd CTA of the last pair may get a tile beyond
     // n_tiles: it still walks the weight stream (TMA zero-fills its patch, its epilogue stores nothing)
     const uint32_t crank = CL ? cluster_ctarank() : 0u;
@@ -136,8 +140,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t aph = 0, bph = 0;
             int bt = 0;                                  // running weight-tile index (same sequence in both CTAs of a cluster)
             for (int tile = tile_first; tile < tile_end; tile += tile_step) {
-                const int n = tile / tiles_per_slice, t2 = tile - n * tiles_per_slice;
-                const int y0 = (t2 / p.tiles_x) * 16, x0 = (t2 % p.tiles_x) * 16;
+                const int txi = tile / tiles_per_tx, t2 = tile - txi * tiles_per_tx;
+                const int n = t2 / p.tiles_y, y0 = (t2 - n * p.tiles_y) * 16, x0 = txi * 16;
                 for (int ch = 0; ch < p.chunks; ++ch) {
                     mbar_wait(a_empty(as), aph ^ 1);
                     mbar_arrive_expect_tx(a_full(as), (SPLIT ? 2 : 1) * 324 * RB);
@@ -177,7 +181,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t d0 = tmem_base + acc * (2 * COUT);
             // the right 8-column sub-tile of a border tile may lie entirely outside the image (24 columns at level 3 = 1.5 tiles):
             // its UMMAs are skipped, and so is its epilogue
-            const int nh = ((tile % p.tiles_x) * 16 + 8 < p.wo) ? 2 : 1;
+            const int nh = ((tile / tiles_per_tx) * 16 + 8 < p.wo) ? 2 : 1;
             for (int ch = 0; ch < p.chunks; ++ch) {
                 mbar_wait(a_full(as), aph);
                 tc_fence_after();
@@ -253,8 +257,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int tile = tile_first; tile < tile_end; tile += tile_step) {
-            const int n = tile / tiles_per_slice, t2 = tile - n * tiles_per_slice;
-            const int oy = (t2 / p.tiles_x) * 16 + ty, x0 = (t2 % p.tiles_x) * 16;
+            const int txi = tile / tiles_per_tx, t2 = tile - txi * tiles_per_tx;
+            const int n = t2 / p.tiles_y, oy = (t2 - n * p.tiles_y) * 16 + ty, x0 = txi * 16;
             mbar_wait(tfull(acc), acc_ph);
             tc_fence_after();
 #pragma unroll 1
