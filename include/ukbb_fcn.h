@@ -22,6 +22,9 @@
  *                             forward over all Z*T slices, D2H of the label volume).
  *   ukbb_fcn_class_counts  <- np.sum(pred == k, axis=(0,1,2)) of deploy_network.py:127-130
  *                             (per-slice class histogram emitted by the classifier).
+ *   ukbb_cc_stats          <- measure.label + per-component np.sum of get_largest_cc / remove_small_cc
+ *                             (common/image_utils.py:227-249) and skimage.measure.label of
+ *                             atrium_pass_quality_control (common/cardiac_utils.py:1629-1640).
  *
  * Conventions
  *   - Plain C, no torch / C++ types.  Every function returns 0 on success and a
@@ -158,6 +161,15 @@ int ukbb_fcn_kernel_timer_read(ukbb_fcn* h, double* total_ms, long long* launche
 long long ukbb_fcn_launch_count(const ukbb_fcn* h);
 int ukbb_fcn_mode(const ukbb_fcn* h);
 int ukbb_fcn_n_class(const ukbb_fcn* h);
+
+/* Connected-component statistics of label maps for the quality-control gates (common/cardiac_utils.py:77-166, 1616-1652;
+ * common/image_utils.py:227-249 get_largest_cc / remove_small_cc).  labels: device uint8 [n_slices][y][x] (x * y < 65535);
+ * classes: HOST int[n_classes] label values; connectivity 1 = faces (scipy.ndimage.label default), 2 = faces + corners
+ * (skimage connectivity=2 in the slice plane).  stats: device int32 [n_slices][n_classes][6] =
+ * {area, components, components with area > thres, largest area, first pixel index of the largest component (-1 if none),
+ *  area kept by remove_small_cc(thres)}.  Asynchronous on `stream`; needs no engine handle. */
+int ukbb_cc_stats(const uint8_t* labels, int n_slices, int x, int y, const int* classes, int n_classes, int connectivity,
+                  int thres, int* stats, void* stream);
 
 /* Host helper (no GPU): Castagnoli CRC used by the TF checkpoint bundle reader. */
 uint32_t ukbb_crc32c(const void* data, size_t n);
