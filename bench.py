@@ -11,6 +11,7 @@ Workloads (BASELINE.json configs; the default is the one the metric is quoted on
     c2  S pairs of long-axis sequences per step: la_2ch (2 classes) + la_4ch (3 classes), 210x171x1x50 -> padded 224x176
     c4  the per-subject segmentation stage with NIfTI in / NIfTI out (sa + la_2ch + la_4ch through the drop-in CLI's deploy()),
         files on local disk; reported in subjects/s (the host I/O stages are part of the measurement)
+    c5  aortic UNet + bidirectional ConvLSTM (network_ao) on one synthetic 240x196x1x100 aortic cine per step (FP32 CUDA-core path)
 
 One step = one pass of the hot path (percentile rescale + pad + build_FCN forward + argmax/crop) over the step's
 sequences.  `value` times the device-resident path (inputs already in HBM); `e2e.value` times the public host-buffer
@@ -145,6 +146,28 @@ def run_reference_arm(args):
         return 0
     from ukbb_cardiac_b200 import synth
     threads = os.cpu_count() or 1
+    if args.workload == "c5":
+        import torch
+        from oracle import ao_oracle as ao
+        torch.set_num_threads(threads)
+        w = synth.make_ao_weights(0)
+        frames = 12
+        vol = np.asfortranarray(synth.make_ao_stack(0)[..., :frames])
+        secs = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            ao.deploy_sequence(vol, w)
+            secs.append(time.perf_counter() - t0)
+        value = frames * args.steps / sum(secs)
+        sample = "%d-frame aortic cine (240x196 padded to 256x256, window 9) per step, reference loop restated with the UNet evaluated once per frame" % frames
+        print(json.dumps({
+            "impl": "reference", "metric": "aortic UNet-LSTM 240x196 frames/sec", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "c5: " + WORKLOAD_NAMES["c5"] + " (CPU sample)", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
+                             "note": "TF-CPU proxy (PyTorch/oneDNN float32 restatement); TensorFlow unavailable"},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
     la = args.workload == "c2"
     shape = LA if la else (SA[0], SA[1], SA[2], args.ref_frames)
     vol = synth.make_stack(0, shape)
@@ -181,6 +204,7 @@ WORKLOAD_NAMES = {
     "c1": "one synthetic SA subject (192x208x10x50) per step, synchronised every step (latency)",
     "c2": "long-axis pairs la_2ch (2 classes) + la_4ch (3 classes), synthetic 210x171x1x50 sequences (padded 224x176)",
     "c4": "per-subject segmentation stage, NIfTI in / NIfTI out: sa + la_2ch + la_4ch .nii.gz per subject through deploy()",
+    "c5": "aortic UNet + BiConvLSTM (network_ao, UNet-LSTM model, window 9, weight_R 5) on one synthetic 240x196x1x100 cine per step",
 }
 
 
@@ -201,6 +225,8 @@ def main():
         return run_reference_arm(args)
     if args.workload == "c4":
         return run_c4(args)
+    if args.workload == "c5":
+        return run_c5(args)
 
     import torch
     import torch.distributed as dist
@@ -418,6 +444,137 @@ def main():
             "cpu_baseline": cpu,
             "parity": parity,
             "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def ao_flops_per_frame(size: int = 256, f0: int = 16, nh: int = 16, n_class: int = 3, window: int = 9) -> float:
+    """Algorithmic FLOPs per OUTPUT frame of the UNet-LSTM deploy loop with the UNet evaluated once per frame:
+    UNet (2 x n^2 x 9 x cin x cout per conv, transposed convs at 2.25 taps per output pixel) + `window` bidirectional ConvLSTM steps
+    (3x3 conv of concat([x, h]) -> 4 nh channels) + the output 1x1 conv."""
+    nf = [f0 * 2 ** i for i in range(5)]
+    total, cin, n = 0.0, 1, size
+    for l in range(5):
+        if l > 0:
+            n //= 2
+        total += 2.0 * n * n * 9 * cin * nf[l] + 2.0 * n * n * 9 * nf[l] * nf[l]
+        cin = nf[l]
+    for l in range(3, -1, -1):
+        n = size >> l
+        total += 2.0 * n * n * 2.25 * nf[l + 1] * nf[l] + 2.0 * n * n * 9 * (2 * nf[l]) * nf[l] + 2.0 * n * n * 9 * nf[l] * nf[l]
+    lstm = window * 2 * (2.0 * size * size * 9 * (f0 + nh) * 4 * nh) + window * 2.0 * size * size * 2 * nh * n_class
+    return total + lstm
+
+
+def run_c5(args):
+    """One synthetic aortic cine (240 x 196 x 1 x 100) per step.  `value`: frames/s with the z-scored, padded cine resident in HBM
+    (ukbb_ao_segment); `e2e`: the public host call (AortaEngine.segment_sequence: z-score on the host as the reference does, pad,
+    H2D, device call, D2H of the labels).  Ranks run independent replicas of the same workload."""
+    import torch
+    import torch.distributed as dist
+    from ukbb_cardiac_b200 import aorta, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+    w = synth.make_ao_weights(0)
+    eng = aorta.AortaEngine(w, device=local)
+    shape = synth.AO_SHAPE
+    X, Y, Z, T = shape
+    vol = synth.make_ao_stack(rank, shape)
+    size = aorta.IMAGE_SIZE
+    x_pre, y_pre = (size - X) // 2, (size - Y) // 2
+    img = np.pad(aorta.normalise_intensity(vol, 10.0), ((x_pre, size - X - x_pre), (y_pre, size - Y - y_pre), (0, 0), (0, 0)), 'constant')
+    d_img = torch.from_numpy(np.ascontiguousarray(np.transpose(img[:, :, 0, :], (2, 1, 0)), dtype=np.float32)).to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    step_dev = lambda: eng.segment_frames(d_img, x_pre, y_pre, X, Y)
+    step_e2e = lambda: eng.segment_sequence(vol)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_dev()
+    l0 = eng.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev = timed(step_dev, args.steps)
+    launches = eng.launch_count - l0
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    value = T * args.steps * world / (ms_dev * 1e-3)
+    e2e_value = T * args.steps * world / (ms_e2e * 1e-3)
+    flop = ao_flops_per_frame(size)
+    achieved = flop * T / (ms_dev / args.steps * 1e-3) / 1e12
+    if rank == 0:
+        cpu = parity = None
+        if args.cpu_frames > 0 and world == 1:
+            import torch as _t
+            from oracle import ao_oracle as ao
+            _t.set_num_threads(os.cpu_count() or 1)
+            frames = 12                                                  # bounded sample: a 12-frame cine at full size
+            sub = np.asfortranarray(vol[..., :frames])
+            t0 = time.perf_counter()
+            pred_ref, _ = ao.deploy_sequence(sub, w)
+            dt = time.perf_counter() - t0
+            pred, _ = eng.segment_sequence(sub)
+            cpu = {"value": frames / dt, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": "%d-frame cine of the same size (240x196, window 9), reference loop restated with the UNet evaluated once per frame, %.1f s" % (frames, dt),
+                   "note": "TF-CPU proxy (PyTorch/oneDNN float32 restatement); TensorFlow unavailable"}
+            parity = {"agreement": float((pred == pred_ref).mean()), "sample": "the same %d-frame cine through the host call vs the float32 CPU restatement" % frames}
+        line = {
+            "metric": "aortic UNet-LSTM 240x196 frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c5: " + WORKLOAD_NAMES["c5"], "frames": T, "padded": "%dx%d" % (size, size), "mode": "fp32 (CUDA cores)",
+                       "weights": "random-init (seed 0), UNet-LSTM checkpoint variable names", "parallelism": "dp%d (replicas)" % world,
+                       "l2_policy": "activations of one cine (> 10 GB) exceed L2 many times over"},
+            "sequences_per_s": value / T,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": T * size * size * 4, "d2h_bytes_per_step": T * X * Y, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp32 FMA pipe (CUDA cores): this path has no tensor-core kernels yet", "achieved": achieved, "unit": "TFLOP/s",
+                         "peak": 75.0, "frac": achieved / 75.0, "peak_source": "B200 FP32 CUDA-core ceiling (~75 TFLOP/s, SURVEY 8d)", "traffic": None,
+                         "algorithmic_flop_per_frame": flop,
+                         "note": "algorithmic FLOPs count the ConvLSTM conv over concat([x, h]); the device evaluates conv(x) once per frame (declared shortcut)"},
+            "cpu_baseline": cpu, "parity": parity, "clocks": sampler.summary(),
         }
         print(json.dumps(line))
     if world > 1:

@@ -171,6 +171,36 @@ int ukbb_fcn_n_class(const ukbb_fcn* h);
 int ukbb_cc_stats(const uint8_t* labels, int n_slices, int x, int y, const int* classes, int n_classes, int connectivity,
                   int thres, int* stats, void* stream);
 
+/* ---- Aortic cine segmentation: UNet + bidirectional ConvLSTM (common/network_ao.py:18-64, 255-319;
+ * common/deploy_network_ao.py:130-183).  FP32 CUDA-core kernels.  ukbb_ao_create <- import_meta_graph + saver.restore
+ * (deploy_network_ao.py:59-60); ukbb_ao_segment <- the whole window loop of deploy_network_ao.py:130-183 (one sess.run per
+ * frame there) incl. the weighted overlap-add, the argmax (:186) and the crop. */
+typedef struct ukbb_ao ukbb_ao;
+
+typedef struct {
+    int n_level;                              /* resolution levels (5), two conv blocks per level (train_network_ao.py:284) */
+    const ukbb_conv_weights* down;            /* 2 * n_level encoder conv + BN layers, graph order (network_ao.py:29-41) */
+    const ukbb_conv_weights* up_transpose;    /* n_level - 1 transposed convs, levels n_level-2 .. 0: kernel in TF's conv2d_transpose
+                                                 layout [3][3][cout][cin], cin = 2 cout, stride 2, + BN (network_ao.py:50-51) */
+    const ukbb_conv_weights* up;              /* 2 * (n_level - 1) decoder conv + BN layers, levels n_level-2 .. 0 (:53-54) */
+    const float* lstm_kernel[2];              /* forward, backward Conv2DLSTMCell kernel [3][3][f0 + n_hidden][4 n_hidden] (:281-297) */
+    const float* lstm_bias[2];                /* [4 n_hidden], gate order (i, j, f, o) */
+    const float* out_kernel;                  /* [2 n_hidden][n_class] (network_ao.py:310) */
+    const float* out_bias;                    /* [n_class] */
+    int n_hidden, n_class;
+    float bn_eps;
+} ukbb_ao_weights;
+
+int ukbb_ao_create(const ukbb_ao_weights* w, int device, ukbb_ao** out);
+void ukbb_ao_destroy(ukbb_ao* h);
+/* image: device float32 [n_frames][y2][x2], z-scored (image_utils.py:60-67) and zero-padded (256 x 256 in the reference,
+ * deploy_network_ao.py:104-107); labels: device uint8 [n_frames][y][x]; prob: optional device float32 [n_frames][y][x][n_class]
+ * = the averaged window probabilities of deploy_network_ao.py:176-180.  weight_R / weight_r: the window flags (5 / 0.1);
+ * the time window is 2 weight_R - 1 frames with circular indexing, time_step 1. */
+int ukbb_ao_segment(ukbb_ao* h, const float* image, int n_frames, int x2, int y2, int x_pre, int y_pre, int x, int y,
+                    int weight_R, double weight_r, uint8_t* labels, float* prob, void* stream);
+long long ukbb_ao_launch_count(const ukbb_ao* h);
+
 /* Host helper (no GPU): Castagnoli CRC used by the TF checkpoint bundle reader. */
 uint32_t ukbb_crc32c(const void* data, size_t n);
 

@@ -58,3 +58,36 @@ def test_cli_process_seq(tmp_path, seq, shape, n_class, mode):
     # second run: everything is skipped (resume rule)
     r2 = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r2.returncode == 0 and "for processing 0 subjects" in r2.stdout
+
+
+def test_cli_aortic(tmp_path):
+    """common/deploy_network_ao.py drop-in: checkpoint bundle with the UNet-LSTM variable names -> CLI -> seg_ao.nii.gz (int32), compared
+    with the CPU restatement of deploy_network_ao.py:83-193 (at the reference's fixed 256 x 256 network input)."""
+    from oracle import ao_oracle as ao
+    w = synth.make_ao_weights(0)
+    tf_bundle.write_bundle(str(tmp_path / "model" / "UNet-LSTM_ao.ckpt-20000"), w)
+    data = tmp_path / "data"
+    vols = {}
+    for i in range(2):
+        d = data / ("200000%d" % i)
+        os.makedirs(d)
+        vols[i] = synth.make_ao_stack(i, (60, 52, 1, 10))
+        img = nifti.Nifti1Image(vols[i], np.diag([1.6, 1.6, 6.0, 1.0]))
+        img.header["pixdim"][4] = 0.01
+        nifti.save(img, str(d / "ao.nii.gz"))
+    os.makedirs(data / "2000009")                                       # a subject without ao.nii.gz
+    cmd = [sys.executable, os.path.join(ROOT, "common", "deploy_network_ao.py"), "--data_dir", str(data),
+           "--model_path", str(tmp_path / "model" / "UNet-LSTM_ao.ckpt-20000")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Start evaluating on the test set ..." in r.stdout and "for processing 2 subjects" in r.stdout
+    assert "does not contain an image with file name ao.nii.gz" in r.stdout
+    for i in range(2):
+        seg_img = nifti.load(str(data / ("200000%d" % i) / "seg_ao.nii.gz"))
+        seg = seg_img.get_data()
+        assert seg.dtype == np.int32 and seg.shape == vols[i].shape
+        assert abs(float(seg_img.header["pixdim"][4]) - 0.01) < 1e-7
+        pred_ref, _ = ao.deploy_sequence(vols[i], w)
+        assert (seg == pred_ref).mean() >= 0.9995
+    r2 = subprocess.run(cmd + ["--noprocess_seq"], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0 and "UNet-LSTM does not support frame-wise segmentation" in r2.stdout

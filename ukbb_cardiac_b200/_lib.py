@@ -59,6 +59,11 @@ SIGNATURES = {
     "ukbb_fcn_n_class": (C.c_int, [C.c_void_p]),
     "ukbb_cc_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                 C.c_void_p]),
+    "ukbb_ao_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ukbb_ao_destroy": (None, [C.c_void_p]),
+    "ukbb_ao_segment": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ukbb_ao_launch_count": (C.c_longlong, [C.c_void_p]),
     "ukbb_crc32c": (C.c_uint32, [C.c_void_p, C.c_size_t]),
     "ukbb_last_error": (C.c_char_p, []),
     "ukbb_version": (C.c_char_p, []),

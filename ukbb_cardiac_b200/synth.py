@@ -95,3 +95,33 @@ def with_optimizer_slots(t: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     out["beta1_power"] = np.asarray(0.9, dtype=np.float32)
     out["beta2_power"] = np.asarray(0.999, dtype=np.float32)
     return out
+
+
+AO_SHAPE = (240, 196, 1, 100)     # BASELINE config C5: synthetic aortic cine
+
+
+def make_ao_weights(seed: int = 0, f0: int = 16, n_hidden: int = 16, n_class: int = 3) -> Dict[str, np.ndarray]:
+    """Random-init weights of the UNet-LSTM aortic model under the checkpoint names of ``aorta.variable_table``: He-scaled kernels,
+    BN statistics around the identity, small LSTM biases, an output bias that gives every class some area."""
+    from . import aorta
+    rng = np.random.default_rng(7000 + seed)
+    w = {}
+    for name, shape in aorta.variable_table(f0, n_hidden, n_class):
+        if name.endswith("kernel"):
+            fan_in = int(np.prod(shape[:2])) * (shape[3] if "conv2d_transpose" in name else shape[2])
+            w[name] = (rng.normal(size=shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+        elif name.endswith("gamma") or name.endswith("moving_variance"):
+            w[name] = rng.uniform(0.8, 1.2, size=shape).astype(np.float32)
+        elif name.endswith("biases"):
+            w[name] = rng.uniform(-0.2, 0.2, size=shape).astype(np.float32)
+        elif name.endswith("bias"):
+            w[name] = rng.uniform(-0.3, 0.3, size=shape).astype(np.float32)
+        else:
+            w[name] = rng.uniform(-0.1, 0.1, size=shape).astype(np.float32) if name.endswith("beta") else rng.normal(0, 0.05, size=shape).astype(np.float32)
+    w["LSTM/output/conv2d/kernel"] *= 6.0          # spread the class scores so that every class covers some area
+    return w
+
+
+def make_ao_stack(seed: int, shape: Tuple[int, int, int, int] = AO_SHAPE) -> np.ndarray:
+    """MR-like aortic cine: the same generator as the SA stacks (pulsating bright discs on a smooth field)."""
+    return make_stack(5000 + seed, shape)
