@@ -150,6 +150,10 @@ int ukbb_fcn_debug_conv(ukbb_fcn* h, int layer, const void* in_bf16, int n, int 
  * 2 = t_level = fc0 column block applied to same_dim_level ([n][h>>level][w>>level][64], level 1..4). */
 int ukbb_fcn_debug_read(ukbb_fcn* h, int which, int level, float* out_f32, long long n_elems, void* stream);
 
+/* Test hook: per-handle switches read by later calls.  bit 0: ukbb_fcn_preprocess / ukbb_fcn_segment_host always take the generic
+ * three-pass radix select instead of the integer fast path (the tests compare the two bit for bit). */
+int ukbb_fcn_debug_flags(ukbb_fcn* h, int flags);
+
 /* Kernel timer used by bench.py for the roofline line: when enabled, every launch of the fused head kernel
  * (the dominant kernel of the forward) is bracketed by CUDA events on the launching stream.
  * ukbb_fcn_kernel_timer_read synchronises the device, returns the summed duration (ms) and the number of

@@ -205,7 +205,7 @@ def _rescale_oracle(arr):
 def test_preprocess_integer_fast_path_and_fallback(monkeypatch, case, shape):
     """Integer-valued volumes take the one-pass counting select + lookup-table rescale; anything else (a negative voxel, a
     fractional one, -0.0, a level above 65535) takes the three-pass radix select on the same call.  Both are bit-exact against
-    the reference arithmetic, and the fast path equals the generic path (UKBB_NO_INT_PATH=1) bit for bit."""
+    the reference arithmetic, and the fast path equals the generic path (ukbb_fcn_debug_flags bit 0) bit for bit."""
     # (37, 29): odd sizes, pad branches, n % 4 tail, scalar rescale; (40, 28) and (64, 48): rows of whole float4s (x_pre = 4 / 0),
     # the table-lookup rescale kernel
     rng = np.random.default_rng(11)
@@ -231,9 +231,8 @@ def test_preprocess_integer_fast_path_and_fallback(monkeypatch, case, shape):
     w = synth.make_weights(0, 2)
     results = []
     for no_int in (False, True):
-        if no_int:
-            monkeypatch.setenv("UKBB_NO_INT_PATH", "1")
         with FCNEngine(w, mode="fp32") as eng:
+            eng.debug_flags(1 if no_int else 0)
             vol = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))).cuda()
             out, vlvh, (x_pre, y_pre) = eng.preprocess(vol, n_slices, x, y, clip_in_place=True)
             torch.cuda.synchronize()

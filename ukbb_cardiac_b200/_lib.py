@@ -52,6 +52,7 @@ SIGNATURES = {
     "ukbb_fcn_debug_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p]),
     "ukbb_fcn_debug_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ukbb_fcn_debug_flags": (C.c_int, [C.c_void_p, C.c_int]),
     "ukbb_fcn_kernel_timer": (C.c_int, [C.c_void_p, C.c_int]),
     "ukbb_fcn_kernel_timer_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ukbb_fcn_launch_count": (C.c_longlong, [C.c_void_p]),

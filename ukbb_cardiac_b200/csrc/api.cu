@@ -397,6 +397,13 @@ int ukbb_fcn_debug_read(ukbb_fcn* hh, int which, int level, float* out_f32, long
     return debug_read_tc(h, which, level, out_f32, n_elems, (cudaStream_t)stream);
 }
 
+int ukbb_fcn_debug_flags(ukbb_fcn* hh, int flags) {
+    Engine* h = reinterpret_cast<Engine*>(hh);
+    UKBB_REQUIRE(h, "debug_flags: null handle");
+    h->pre.no_int_path = (flags & 1) ? 1 : 0;
+    return UKBB_OK;
+}
+
 int ukbb_fcn_kernel_timer(ukbb_fcn* hh, int enable) {
     ukbb::Engine* h = reinterpret_cast<ukbb::Engine*>(hh);
     if (!h) { ukbb::set_error("kernel_timer: null handle"); return UKBB_E_INVALID; }

@@ -56,6 +56,7 @@ struct PreprocWorkspace {
     double* vlvh = nullptr;            // device (vl, vh)
     float* sel = nullptr;              // 4 selected order statistics
     float* lut = nullptr;              // integer fast path: rescaled value per level (65536 + 2)
+    int no_int_path = 0;               // test hook (ukbb_fcn_debug_flags bit 0): always take the generic radix select
 };
 int preproc_alloc(PreprocWorkspace& ws);
 void preproc_free(PreprocWorkspace& ws);

@@ -434,7 +434,7 @@ int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int hgrid = sms * 4;       // 4 resident 512-thread CTAs per SM
     sel_init_kernel<<<16, 256, 0, st>>>(state, ws.hist, rk[0], rk[1], rk[2], rk[3]);
-    if (!getenv("UKBB_NO_INT_PATH")) {
+    if (!ws.no_int_path) {
         int_hist_kernel<<<hgrid, 512, 0, st>>>(vol, n, ws.hist, state);
         int_scan_kernel<<<1, 1024, 0, st>>>(state, ws.hist);
         if (launches) *launches += 2;
@@ -448,7 +448,7 @@ int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int 
     sel_final_kernel<<<1, 32, 0, st>>>(state, t[0], t[1], ws.vlvh, ws.sel, vl_vh_out);
     lut_kernel<<<32, 256, 0, st>>>(state, ws.vlvh, ws.lut);
     const long long total4 = n_slices * y2 * (x2 / 4);
-    const int vec_rows = ((x | x_pre) & 3) == 0 && n_slices <= 65535 && !getenv("UKBB_NO_INT_PATH");
+    const int vec_rows = ((x | x_pre) & 3) == 0 && n_slices <= 65535 && !ws.no_int_path;
     if (vec_rows) {
         const int xq = x2 >> 2, bx = xq >= 64 ? 64 : (xq + 15) / 16 * 16, by = 256 / bx;
         dim3 block(bx, by), grid((xq + bx - 1) / bx, (y2 + by - 1) / by, (unsigned)n_slices);

@@ -343,6 +343,10 @@ class FCNEngine:
             _lib.check(self.lib.ukbb_fcn_debug_read(self._h, which, level, out.data_ptr(), out.numel(), self._stream()))
         return out
 
+    def debug_flags(self, flags: int) -> None:
+        """Test hook: bit 0 = always take the generic radix select in the percentile rescale (no integer fast path)."""
+        _lib.check(self.lib.ukbb_fcn_debug_flags(self._h, int(flags)))
+
     def kernel_timer(self, enable: bool) -> None:
         """Bracket every launch of the fused head kernel with CUDA events on the launching stream (bench.py roofline)."""
         _lib.check(self.lib.ukbb_fcn_kernel_timer(self._h, 1 if enable else 0))
