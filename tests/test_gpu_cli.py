@@ -91,3 +91,28 @@ def test_cli_aortic(tmp_path):
         assert (seg == pred_ref).mean() >= 0.9995
     r2 = subprocess.run(cmd + ["--noprocess_seq"], capture_output=True, text=True, timeout=300)
     assert r2.returncode == 0 and "UNet-LSTM does not support frame-wise segmentation" in r2.stdout
+
+
+def test_cli_native_int16_volume(tmp_path):
+    """A short-axis file stored as int16 (round-1 advisor finding): the reference computes the percentiles and clips IN PLACE in the
+    file's dtype, so the thresholds are truncated on assignment and the saved <seq>_ED/ES frames are int16; the drop-in reproduces
+    both (host arithmetic of image_utils.py:70-77 for such files, network on the device)."""
+    seq, shape = "sa", (40, 52, 3, 4)
+    w = synth.make_weights(0, 4)
+    tf_bundle.write_bundle(str(tmp_path / "model" / "FCN_sa"), w)
+    d = tmp_path / "data" / "1000000"
+    os.makedirs(d)
+    vol = synth.make_stack(21, shape).astype(np.int16)
+    nifti.save(nifti.Nifti1Image(np.asfortranarray(vol), np.diag([1.8, 1.8, 10.0, 1.0])), str(d / "sa.nii.gz"))
+    cmd = [sys.executable, os.path.join(ROOT, "common", "deploy_network.py"), "--seq_name", seq, "--data_dir", str(tmp_path / "data"),
+           "--model_path", str(tmp_path / "model" / "FCN_sa"), "--mode", "fp32"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref_in = np.array(vol, order="F")                                  # int16, clipped in place by the restated reference loop
+    pred_ref, clipped = do.deploy_sequence(ref_in, do.make_runner(w))
+    assert clipped.dtype == np.int16
+    seg = nifti.load(str(d / "seg_sa.nii.gz")).get_data()
+    assert (seg == pred_ref).mean() >= 1 - 2e-5
+    ed = nifti.load(str(d / "sa_ED.nii.gz")).get_data()
+    assert ed.dtype == np.int16
+    np.testing.assert_array_equal(ed, clipped[:, :, :, 0])

@@ -135,6 +135,19 @@ def _as_float32(image: np.ndarray) -> np.ndarray:
     return image if image.dtype == np.float32 else image.astype(np.float32)
 
 
+def rescale_intensity_native(image: np.ndarray, thres=(1.0, 99.0)):
+    """image_utils.py:70-77 verbatim, for volumes whose dtype is NOT float32: the reference clips its input array IN PLACE in the
+    file's native dtype, so for an integer volume the thresholds are truncated on assignment (vl = 12.7 is stored as 12) before the
+    float32 rescale, and a float64 volume (scl_slope set) is clipped in float64.  The device path assumes float32 voxels, so these
+    volumes take the reference's own arithmetic on the host and only the network runs on the device.  Returns (rescaled array,
+    the clipped input = what the reference saves as <seq>_ED/ES.nii.gz, vl, vh)."""
+    val_l, val_h = np.percentile(image, thres)
+    image2 = image
+    image2[image < val_l] = val_l
+    image2[image > val_h] = val_h
+    return (image2.astype(np.float32) - val_l) / (val_h - val_l), image2, val_l, val_h
+
+
 class _SyncEngine:
     """Adapter for engines that only offer the synchronous `segment_volume` (tests' stub): same ticket protocol as FCNEngine."""
 
@@ -305,8 +318,36 @@ def deploy(flags: Flags, engine=None, out=sys.stdout, stage_times: Optional[Dict
                         say(ln)
                     say("  Error: {0} is not a 4-D sequence (shape {1}). Skip.".format(image_name, image.shape))
                     continue
-                image = _as_float32(image)
                 lines.append("  Segmenting full sequence ...")         # :85
+                if image.dtype != np.float32 and hasattr(engine, "segment_rescaled"):
+                    # native-dtype volume: the reference's host arithmetic for the rescale (see rescale_intensity_native), synchronous
+                    while pending:
+                        finish(pending.pop(0))
+                    start_seg_time = time.time()
+                    image2, clipped, _, _ = rescale_intensity_native(np.array(image, order="F"))
+                    labels, counts = engine.segment_rescaled(image2)
+                    seg_time = time.time() - start_seg_time
+                    lines.append("  Segmentation time = {:3f}s".format(seg_time))
+                    table_time.append(seg_time)
+                    processed_list.append(data)
+                    k = {"ED": 0, "ES": es_frame_from_counts(counts, flags.seq_name, flags.seg4)}
+                    lines.append("  ED frame = {:d}, ES frame = {:d}".format(k["ED"], k["ES"]))
+                    if flags.save_seg:
+                        lines.append("  Saving segmentation ...")
+                        nim2 = nifti.Nifti1Image(labels, nim.affine)
+                        nim2.header["pixdim"] = nim.header["pixdim"]
+                        nifti.save(nim2, "{0}/{1}_{2}.nii.gz".format(data_dir, prefix, flags.seq_name), dtype=label_dt, label_data=True)
+                        for fr in ("ED", "ES"):                        # the clipped frames keep the file's dtype, like orig_image in the reference
+                            nifti.save(nifti.Nifti1Image(np.asfortranarray(clipped[:, :, :, k[fr]]), nim.affine),
+                                       "{0}/{1}_{2}.nii.gz".format(data_dir, flags.seq_name, fr))
+                            nifti.save(nifti.Nifti1Image(np.asfortranarray(labels[:, :, :, k[fr]]), nim.affine),
+                                       "{0}/{1}_{2}_{3}.nii.gz".format(data_dir, prefix, flags.seq_name, fr), dtype=label_dt, label_data=True)
+                    for b_ in bufs:
+                        eng.release_host_buffer(b_)
+                    for ln in lines:
+                        say(ln)
+                    continue
+                image = _as_float32(image)
                 t_submit = time.time()
                 ticket = eng.submit_volume(image)
                 pending.append((lines, data, data_dir, nim, image, bufs, ticket, t_submit))

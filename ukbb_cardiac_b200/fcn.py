@@ -252,6 +252,26 @@ class FCNEngine:
                 ticket[k] = None
         ticket["keep"] = None
 
+    def segment_rescaled(self, image2: np.ndarray):
+        """Segment an ALREADY rescaled image (X, Y[, Z[, T]]) -- the array `rescale_intensity` returned, before the padding of
+        deploy_network.py:97-100 -- without the device percentile pass.  Used for inputs whose native dtype is not float32, where
+        the reference's in-place clipping truncates the thresholds to that dtype (deploy.py).  Returns (labels uint8, same shape,
+        Fortran order; counts int64 [T, Z, n_class])."""
+        shp = tuple(image2.shape)
+        x, y = shp[0], shp[1]
+        z = shp[2] if image2.ndim >= 3 else 1
+        t = shp[3] if image2.ndim == 4 else 1
+        x2, x_pre = pad16(x)
+        y2, y_pre = pad16(y)
+        vol = np.asarray(image2, dtype=np.float32).reshape((x, y, z * t), order="F")
+        padded = np.zeros((z * t, y2, x2), dtype=np.float32)
+        padded[:, y_pre:y_pre + y, x_pre:x_pre + x] = np.transpose(vol, (2, 1, 0))
+        dev = torch.from_numpy(padded).to(self.device)
+        labels, _, _ = self.forward(dev, x_pre, y_pre, x, y)
+        counts = self.class_counts(z * t).cpu().numpy().reshape(t, z, self.n_class)
+        lab = np.transpose(labels.cpu().numpy(), (2, 1, 0)).reshape(shp, order="F")
+        return np.asfortranarray(lab), counts
+
     def segment_volume(self, image: np.ndarray, q: Sequence[float] = (1.0, 99.0)):
         """image: (X, Y, Z, T), (X, Y, Z) or (X, Y) array as returned by ``nim.get_data()``.
         Returns (labels uint8 array of the same shape, Fortran order, (vl, vh), counts
