@@ -5,10 +5,12 @@ import collections, gzip, re, sys
 path = sys.argv[1]
 out_dir = sys.argv[2] if len(sys.argv) > 2 else None
 KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "FFMA2", "FADD2", "F2FP", "LDG", "STG", "LDS", "STS", "REDG"]
-DEFAULT = ["conv_first_tc_kernelILb0", "conv_first_kernelILb0", "conv_group_kernelILi16ELi32ELi2ELb0", "conv_group_kernelILi32ELi32ELi1ELb0", "conv_group_kernelILi32ELi64ELi2ELb0",
-           "conv_group_kernelILi64ELi64ELi1ELb0", "conv_tc_kernelILi64ELi128ELb0", "conv_tc_kernelILi64ELi256ELb0",
-           "conv_halo_kernelILi64ELi128ELb0ELi0ELb0ELb1", "conv_halo_kernelILi64ELi256ELb0ELi0ELb0ELb1", "side_tc_kernelILb0", "head_ts_kernelILi4ELb0",
-           "sel_hist0", "sel_histn", "sel_scan", "sel_final", "sel_init", "rescale_pad"]
+# kernels on the DEFAULT path (mode fp16x3: F16 = true, SPLIT = true template flags)
+DEFAULT = ["conv_first_tc_kernelILb1ELb1", "conv_group_kernelILi16ELi32ELi2ELb1ELb1", "conv_group_kernelILi32ELi32ELi1ELb1ELb1",
+           "conv_group_kernelILi32ELi64ELi2ELb1ELb1", "conv_group_kernelILi64ELi64ELi1ELb1ELb1", "conv_tc_kernelILi64ELi128ELb1ELb1",
+           "conv_tc_kernelILi64ELi256ELb1ELb1", "conv_halo_kernelILi32ELi128ELb0ELi0ELb1ELb1ELb1", "conv_halo_kernelILi32ELi256ELb0ELi0ELb1ELb1ELb1",
+           "side_tc_kernelILb1ELb1", "head_ts_kernelILi4ELb1ELb1", "int_hist", "int_scan", "lut_kernel", "rescale_lut", "sel_hist0", "sel_histn",
+           "sel_scan", "sel_final", "sel_init", "rescale_pad", "cc_stats_kernel", "convT_fp32", "lstm_point", "ao_output", "conv_fp32_kernel"]
 cur, funcs = None, collections.OrderedDict()
 for line in open(path, errors="replace"):
     m = re.search(r"Function : (\S+)", line)
@@ -31,7 +33,7 @@ for name, lines in funcs.items():
                 ops[k] += 1
     print("%-78s %6d " % (name[:78], n) + " ".join("%7d" % ops[k] for k in KEYS))
 if out_dir:
-    with gzip.open(out_dir + "/r1_sass_default_path_kernels.txt.gz", "wt") as f:
+    with gzip.open(out_dir + "/r2_sass_default_path_kernels.txt.gz", "wt") as f:
         for name, lines in funcs.items():
             if any(d in name for d in DEFAULT):
                 f.write("Function : %s\n" % name)
