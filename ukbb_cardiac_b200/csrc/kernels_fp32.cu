@@ -10,17 +10,110 @@
 namespace ukbb {
 
 // ------------------------------------------------------------------------------------------
-// Direct convolution, register-tiled: one thread = one output pixel x CB output channels.
-// Block = 8 x 16 output pixels (128 threads); the input patch of CC channels is staged in
-// shared memory channel-major so that a warp reads consecutive pixels (no bank conflicts
-// at stride 1, 2-way at stride 2); weights of the chunk are staged [tap][c][CB] and read as
-// broadcast float4.
+// Direct convolution, register-tiled: one thread = a 2 x 2 block of output pixels x CB output channels.
+// Block = 16 x 32 output pixels (128 threads); the input patch of CC channels is staged in shared memory
+// channel-major; weights of the chunk are staged [tap][c][CB] and read as broadcast float4.  Per input
+// channel a thread reads its (S + KS) x (S + KS) input window once (16 or 25 LDS) and the KS x KS x 4 weight
+// vectors once for 4 x KS x KS x CB FMAs: ~13 FMAs per shared-memory load (the first version of this kernel,
+// one pixel per thread, issued 5 loads per 16 FMAs and ran at 12 TFLOP/s).  Every output accumulates its
+// products in the same order as before (chunk, ky, kx, c), so results are bit-identical to that version.
 // ------------------------------------------------------------------------------------------
-constexpr int TH = 8, TW = 16, CB = 16;
+constexpr int TH = 8, TW = 16, CB = 16;          // threads per block: TH x TW, each owning 2 x 2 pixels
+constexpr int OH = 2 * TH, OW = 2 * TW;          // output pixels per block: 16 x 32
 
 template <int KS, int S, int CC>
 __global__ void __launch_bounds__(TH* TW)
 conv_fp32_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ wt,
+                 const float* __restrict__ scale, const float* __restrict__ shift, int cin, int cout,
+                 int hi, int wi, int ho, int wo, int pad_top, int pad_left, int tiles_x, int relu) {
+    constexpr int PH = (OH - 1) * S + KS, PW = (OW - 1) * S + KS;
+    constexpr int WIN = S + KS;                  // input window of a 2 x 2 output block (per axis)
+    __shared__ float s_in[CC][PH * PW];
+    __shared__ __align__(16) float s_w[KS * KS][CC][CB];
+
+    const int tid = threadIdx.x;
+    const int px = tid % TW, py = tid / TW;
+    const int tile = blockIdx.x;
+    const int ox0 = (tile % tiles_x) * OW, oy0 = (tile / tiles_x) * OH;
+    const int cb0 = blockIdx.y * CB;
+    const int n = blockIdx.z;
+    const int iy0 = oy0 * S - pad_top, ix0 = ox0 * S - pad_left;
+
+    float acc[4][CB];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < CB; ++j) acc[q][j] = 0.f;
+
+    const float* in_n = in + (size_t)n * hi * wi * cin;
+    for (int c0 = 0; c0 < cin; c0 += CC) {
+        for (int e = tid; e < PH * PW * CC; e += TH * TW) {
+            const int c = e % CC, pix = e / CC;
+            const int gy = iy0 + pix / PW, gx = ix0 + pix % PW;
+            float v = 0.f;
+            if (gy >= 0 && gy < hi && gx >= 0 && gx < wi) v = in_n[((size_t)gy * wi + gx) * cin + c0 + c];
+            s_in[c][pix] = v;
+        }
+        for (int e = tid; e < KS * KS * CC * CB; e += TH * TW) {
+            const int j = e % CB, c = (e / CB) % CC, tap = e / (CB * CC);
+            s_w[tap][c][j] = wt[((size_t)tap * cin + c0 + c) * cout + cb0 + j];
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int c = 0; c < CC; ++c) {
+            float v[WIN][WIN];
+            const float* base = &s_in[c][(2 * py * S) * PW + 2 * px * S];
+#pragma unroll
+            for (int r = 0; r < WIN; ++r)
+#pragma unroll
+                for (int k = 0; k < WIN; ++k) v[r][k] = base[r * PW + k];
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
+                    const float4* w4 = reinterpret_cast<const float4*>(&s_w[ky * KS + kx][c][0]);
+#pragma unroll
+                    for (int q4 = 0; q4 < CB / 4; ++q4) {
+                        const float4 w = w4[q4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float x = v[(q >> 1) * S + ky][(q & 1) * S + kx];
+                            acc[q][4 * q4 + 0] = fmaf(x, w.x, acc[q][4 * q4 + 0]);
+                            acc[q][4 * q4 + 1] = fmaf(x, w.y, acc[q][4 * q4 + 1]);
+                            acc[q][4 * q4 + 2] = fmaf(x, w.z, acc[q][4 * q4 + 2]);
+                            acc[q][4 * q4 + 3] = fmaf(x, w.w, acc[q][4 * q4 + 3]);
+                        }
+                    }
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int oy = oy0 + 2 * py + (q >> 1), ox = ox0 + 2 * px + (q & 1);
+        if (oy < ho && ox < wo) {
+            float* o = out + (((size_t)n * ho + oy) * wo + ox) * cout + cb0;
+#pragma unroll
+            for (int q4 = 0; q4 < CB / 4; ++q4) {
+                float4 r;
+                r.x = fmaf(acc[q][4 * q4 + 0], scale[cb0 + 4 * q4 + 0], shift[cb0 + 4 * q4 + 0]);
+                r.y = fmaf(acc[q][4 * q4 + 1], scale[cb0 + 4 * q4 + 1], shift[cb0 + 4 * q4 + 1]);
+                r.z = fmaf(acc[q][4 * q4 + 2], scale[cb0 + 4 * q4 + 2], shift[cb0 + 4 * q4 + 2]);
+                r.w = fmaf(acc[q][4 * q4 + 3], scale[cb0 + 4 * q4 + 3], shift[cb0 + 4 * q4 + 3]);
+                if (relu) {
+                    r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+                }
+                reinterpret_cast<float4*>(o)[q4] = r;
+            }
+        }
+    }
+}
+
+// The first version of the kernel: one thread = ONE output pixel x CB channels, block = 8 x 16 pixels.  Kept for small feature maps
+// (levels 3 / 4 of a short-axis slice are 24 x 26 and 12 x 13 pixels: a 16 x 32 tile would be mostly padding there).
+template <int KS, int S, int CC>
+__global__ void __launch_bounds__(TH* TW)
+conv_fp32_px_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ wt,
                  const float* __restrict__ scale, const float* __restrict__ shift, int cin, int cout,
                  int hi, int wi, int ho, int wo, int pad_top, int pad_left, int tiles_x, int relu) {
     constexpr int PH = (TH - 1) * S + KS, PW = (TW - 1) * S + KS;
@@ -94,16 +187,16 @@ int launch_conv_fp32(const float* in, float* out, const ConvLayer& L, int n, int
                      int wo, int pad_top, int pad_left, cudaStream_t st) {
     UKBB_REQUIRE(L.cout % CB == 0, "conv_fp32: cout=%d is not a multiple of %d", L.cout, CB);
     UKBB_REQUIRE(L.cin == 1 || L.cin % 8 == 0, "conv_fp32: cin=%d must be 1 or a multiple of 8", L.cin);
-    const int tiles_x = (wo + TW - 1) / TW, tiles_y = (ho + TH - 1) / TH;
+    const bool big = wo >= 48 && ho >= 24;            // 2 x 2 pixels per thread, 16 x 32 tiles
+    const int tw = big ? OW : TW, th = big ? OH : TH;
+    const int tiles_x = (wo + tw - 1) / tw, tiles_y = (ho + th - 1) / th;
     dim3 grid(tiles_x * tiles_y, L.cout / CB, n), block(TH * TW);
-#define LAUNCH(KS, S, CC)                                                                         \
-    conv_fp32_kernel<KS, S, CC><<<grid, block, 0, st>>>(in, out, L.w_f32, L.scale, L.shift, L.cin, \
-                                                        L.cout, hi, wi, ho, wo, pad_top, pad_left, \
-                                                        tiles_x, L.relu)
-    if (L.ksize == 3 && L.stride == 1 && L.cin == 1) LAUNCH(3, 1, 1);
-    else if (L.ksize == 3 && L.stride == 1) LAUNCH(3, 1, 8);
-    else if (L.ksize == 3 && L.stride == 2) LAUNCH(3, 2, 8);
-    else if (L.ksize == 1 && L.stride == 1) LAUNCH(1, 1, 8);
+#define LAUNCH(KERN, KS, S, CC)                                                                   \
+    KERN<KS, S, CC><<<grid, block, 0, st>>>(in, out, L.w_f32, L.scale, L.shift, L.cin, L.cout, hi, wi, ho, wo, pad_top, pad_left, tiles_x, L.relu)
+    if (L.ksize == 3 && L.stride == 1 && L.cin == 1) { if (big) LAUNCH(conv_fp32_kernel, 3, 1, 1); else LAUNCH(conv_fp32_px_kernel, 3, 1, 1); }
+    else if (L.ksize == 3 && L.stride == 1) { if (big) LAUNCH(conv_fp32_kernel, 3, 1, 8); else LAUNCH(conv_fp32_px_kernel, 3, 1, 8); }
+    else if (L.ksize == 3 && L.stride == 2) { if (big) LAUNCH(conv_fp32_kernel, 3, 2, 4); else LAUNCH(conv_fp32_px_kernel, 3, 2, 8); }
+    else if (L.ksize == 1 && L.stride == 1) { if (big) LAUNCH(conv_fp32_kernel, 1, 1, 8); else LAUNCH(conv_fp32_px_kernel, 1, 1, 8); }
     else {
         set_error("conv_fp32: unsupported ksize=%d stride=%d cin=%d", L.ksize, L.stride, L.cin);
         return UKBB_E_UNSUPPORTED;
