@@ -5,6 +5,7 @@ Follows
     structure = face connectivity; the FIRST label wins ties of the largest area; components with area < thres are removed)
   * ``common/cardiac_utils.py:77-136``   sa_pass_quality_control
   * ``common/cardiac_utils.py:137-166``  la_pass_quality_control
+  * ``common/cardiac_utils.py:1739-1795`` aorta_pass_quality_control (same labelling call)
   * ``common/cardiac_utils.py:1616-1652`` atrium_pass_quality_control (``skimage.measure.label(mask, connectivity=2)`` on an
     (X, Y, Z) array: neighbours sharing a face or an edge; scikit-image is absent here, the same labelling is obtained from
     ``scipy.ndimage.label`` with ``generate_binary_structure(3, 2)``)
@@ -91,4 +92,30 @@ def atrium_pass_quality_control(label: np.ndarray, label_dict) -> bool:
             ratio = A[t] / float(A[t - 1])
             if ratio >= 2 or ratio <= 0.5:
                 return False
+    return True
+
+
+def aorta_pass_quality_control(image: np.ndarray, seg: np.ndarray) -> bool:
+    """cardiac_utils.py:1739-1795 (skimage.measure.label(connectivity=2) restated with scipy, see the module docstring)."""
+    structure = ndimage.generate_binary_structure(3, 2)
+    for l in (1, 2):
+        T = seg.shape[3]
+        for t in range(T):
+            if np.sum(seg[:, :, :, t] == l) == 0:
+                return False
+        mean_intensity_ED = image[:, :, :, 0][seg[:, :, :, 0] == l].mean()
+        for t in range(T):
+            if np.max(image[:, :, :, t][seg[:, :, :, t] == l]) / mean_intensity_ED >= 3:
+                return False
+        for t in range(T):
+            cc, n_cc = ndimage.label(seg[:, :, :, t] == l, structure=structure)
+            if sum(1 for i in range(1, n_cc + 1) if np.sum(cc == i) > 10) >= 2:
+                return False
+        A = np.sum(seg == l, axis=(0, 1, 2))
+        for t in range(T):
+            ratio = A[t] / float(A[t - 1])
+            if ratio >= 2 or ratio <= 0.5:
+                return False
+        if np.max(A) / np.min(A) >= 2:
+            return False
     return True

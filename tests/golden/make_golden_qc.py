@@ -100,10 +100,10 @@ def la_slice(rng, X=64, Y=56, drop=None, frag_myo=False):
     return seg
 
 
-def atrium_seq(rng, X=48, Y=40, T=12, vanish=None, fragment=None, jump=None, diag=False):
+def atrium_seq(rng, X=48, Y=40, T=12, vanish=None, fragment=None, jump=None, diag=False, amp=2.0):
     lab = np.zeros((X, Y, 1, T), dtype=np.int16)
     for t in range(T):
-        r = 7 + 2 * np.sin(2 * np.pi * t / T)
+        r = 7 + amp * np.sin(2 * np.pi * t / T)
         if jump is not None and t == jump:
             r *= 1.7
         lab[:, :, 0, t][disc(X, Y, 16, 14, r)] = 1
@@ -153,6 +153,23 @@ def main():
         lab = atrium_seq(rng, **kw)
         out["at_" + name] = lab
         out["at_verdict_" + name] = np.array(bool(cu.atrium_pass_quality_control(lab, {'LA': 1, 'RA': 2})))
+    for name, kw in {"good": {}, "vanish": {"vanish": 5}, "fragment": {"fragment": 7}, "jump": {"jump": 4}, "noisy": {}, "breathing": {}}.items():
+        lab = atrium_seq(rng, amp=0.8, **kw)
+        if name == "breathing":                      # slow growth: adjacent ratios fine, max / min >= 2
+            lab[:] = 0
+            for t in range(lab.shape[3]):
+                r = 5.0 + 0.32 * (t if t <= 6 else 12 - t)
+                lab[:, :, 0, t][disc(48, 40, 16, 14, r)] = 1
+                lab[:, :, 0, t][disc(48, 40, 32, 26, 6)] = 2
+        img = (200 + 30 * rng.standard_normal(lab.shape)).astype(np.float32)
+        img[lab == 1] += 300
+        img[lab == 2] += 250
+        if name == "noisy":
+            xs = np.argwhere(lab[:, :, 0, 6] == 2)[0]
+            img[xs[0], xs[1], 0, 6] = 2500.0
+        out["ao_seg_" + name] = lab
+        out["ao_img_" + name] = img
+        out["ao_verdict_" + name] = np.array(bool(cu.aorta_pass_quality_control(img, lab)))
     np.savez_compressed(os.path.join(HERE, "qc_reference.npz"), **out)
     for k in sorted(out):
         if "verdict" in k:

@@ -17,10 +17,11 @@ GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"
 SA = sorted(k[len("sa_verdict_"):] for k in GOLD.files if k.startswith("sa_verdict_"))
 LA = sorted(k[len("la_verdict_"):] for k in GOLD.files if k.startswith("la_verdict_"))
 AT = sorted(k[len("at_verdict_"):] for k in GOLD.files if k.startswith("at_verdict_"))
+AO = sorted(k[len("ao_verdict_"):] for k in GOLD.files if k.startswith("ao_verdict_"))
 
 
 def test_golden_covers_both_verdicts():
-    for names, pre in ((SA, "sa"), (LA, "la"), (AT, "at")):
+    for names, pre in ((SA, "sa"), (LA, "la"), (AT, "at"), (AO, "ao")):
         verdicts = {bool(GOLD["%s_verdict_%s" % (pre, n)]) for n in names}
         assert verdicts == {True, False}, pre
 
@@ -39,6 +40,8 @@ def test_oracle_gates_match_reference(capsys):
         assert qo.la_pass_quality_control(GOLD["la_" + n]) == bool(GOLD["la_verdict_" + n]), n
     for n in AT:
         assert qo.atrium_pass_quality_control(GOLD["at_" + n], {'LA': 1, 'RA': 2}) == bool(GOLD["at_verdict_" + n]), n
+    for n in AO:
+        assert qo.aorta_pass_quality_control(GOLD["ao_img_" + n], GOLD["ao_seg_" + n]) == bool(GOLD["ao_verdict_" + n]), n
 
 
 # ------------------------------------------------------------------------------------------ GPU
@@ -91,6 +94,8 @@ def test_product_gates_match_reference(capsys):
         assert qc.la_pass_quality_control(GOLD["la_" + n]) == bool(GOLD["la_verdict_" + n]), n
     for n in AT:
         assert qc.atrium_pass_quality_control(GOLD["at_" + n], {'LA': 1, 'RA': 2}) == bool(GOLD["at_verdict_" + n]), n
+    for n in AO:
+        assert qc.aorta_pass_quality_control(GOLD["ao_img_" + n], GOLD["ao_seg_" + n]) == bool(GOLD["ao_verdict_" + n]), n
     out = capsys.readouterr().out
     assert "There is missing segmentation between the slices." in out and "abrupt change of area at time frame" in out
 

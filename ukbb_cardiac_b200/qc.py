@@ -4,6 +4,7 @@ wall-thickness / strain / atrial-volume stages of the reference pipeline.
   sa_pass_quality_control      common/cardiac_utils.py:77-136   (short_axis/eval_wall_thickness.py:43, eval_strain_sax.py:46)
   la_pass_quality_control      common/cardiac_utils.py:137-166  (long_axis/eval_strain_lax.py:46)
   atrium_pass_quality_control  common/cardiac_utils.py:1616-1652 (long_axis/eval_atrial_volume.py:66,102)
+  aorta_pass_quality_control   common/cardiac_utils.py:1739-1795 (aortic/eval_aortic_area.py:68)
 
 Same names, arguments, printed messages and verdicts as the reference.  The per-slice, per-class connected-component
 statistics (area, number of components above the pixel threshold, largest component, area kept by remove_small_cc) come from
@@ -152,4 +153,40 @@ def atrium_pass_quality_control(label: np.ndarray, label_dict: Dict[str, int], d
             if ratio >= 2 or ratio <= 0.5:
                 print('There is abrupt change of area at time frame {0}.'.format(t))
                 return False
+    return True
+
+
+def aorta_pass_quality_control(image: np.ndarray, seg: np.ndarray, device=0) -> bool:
+    """Quality control for aortic segmentation (cardiac_utils.py:1739-1795): image, seg (X, Y, 1, T).  Areas, fragment counts
+    (8-connected) and the area ratios of all T frames and both vessels come from one device launch; the intensity criterion
+    (max within the vessel vs the ED mean) is a masked reduction of the image on the host."""
+    image, seg = np.asarray(image), np.asarray(seg)
+    if seg.shape[2] != 1:
+        raise ValueError("aorta_pass_quality_control expects single-slice aortic label maps (X, Y, 1, T)")
+    T = seg.shape[3]
+    st = cc_stats(_device_slices(seg[:, :, 0, :], torch.device("cuda", device)), [1, 2], connectivity=2)    # [T, 2, 6]
+    for i, (l_name, l) in enumerate([('AAo', 1), ('DAo', 2)]):
+        A = st[:, i, 0].astype(np.int64)
+        for t in range(T):                                                                        # criterion 1 (:1742-1749)
+            if A[t] == 0:
+                print('The area of {0} is 0 at time frame {1}.'.format(l_name, t))
+                return False
+        mean_intensity_ED = image[:, :, :, 0][seg[:, :, :, 0] == l].mean()                          # criterion 2 (:1751-1763)
+        for t in range(T):
+            if np.max(image[:, :, :, t][seg[:, :, :, t] == l]) / mean_intensity_ED >= 3:
+                print('The image becomes very noisy at time frame {0}.'.format(t))
+                return False
+        for t in range(T):                                                                        # criterion 3 (:1765-1780)
+            if st[t, i, 2] >= 2:
+                print('The segmentation has at least two connected components with more than {0} pixels '
+                      'at time frame {1}.'.format(PIXEL_THRES, t))
+                return False
+        for t in range(T):                                                                        # criterion 4 (:1782-1788)
+            ratio = A[t] / float(A[t - 1])
+            if ratio >= 2 or ratio <= 0.5:
+                print('There is abrupt change of area at time frame {0}.'.format(t))
+                return False
+        if np.max(A) / np.min(A) >= 2:                                                            # criterion 5 (:1790-1794)
+            print('There is large change of area between maximum and minimum areas.')
+            return False
     return True
