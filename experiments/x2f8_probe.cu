@@ -1,0 +1,161 @@
+// Probe for a cheaper split scheme (round 2): main term in FP16 (kind::f16) + BOTH correction terms in ONE FP8 pass (kind::f8f6f4, K = 32
+// per instruction = the same 32 bytes per row as an FP16 K = 16 step):
+//     D = A_hi.B_hi  +  2^-15 * ( [a_lo 2^11 | a_hi]_e4m3 . [w_hi 2^4 | w_lo 2^15]_e4m3 )
+// with the 2^-15 applied by `scale-input-d` of the FIRST kind::f16 instruction (D <- A.B + D * 2^-15), so that one accumulator serves both.
+// Questions: do UTCQMMA with these descriptors / idesc and scale-input-d do what the PTX ISA says on sm_100a, and how accurate is it?
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -I ukbb_cardiac_b200/csrc experiments/x2f8_probe.cu -o experiments/bin/x2f8_probe
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include "tc_common.cuh"
+using namespace ukbb::tc;
+
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f16_scaled(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {     // D = A.B + D * 2^-15
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 15;\n}\n" ::"r"(tmem_d), "l"(adesc),
+                 "l"(bdesc), "r"(idesc) : "memory");
+}
+
+// global: A16 [128][64] fp16 | A8 [128][128] e4m3 ; B16 [64][64] fp16 | B8 [64][128] e4m3  (all rows 128 bytes, SWIZZLE_128B)
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int mode, float* out) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    const uint32_t a16 = base, a8 = base + 16384, b16 = base + 32768, b8 = base + 32768 + 8192;
+    const uint32_t bar = base + 49152, bar2 = bar + 8, slot = bar + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
+    if (warp == 1) { tmem_alloc(slot, 64); tmem_relinquish(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    uint32_t tmem; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, 2 * 16384 + 2 * 8192);
+        tma_load_2d(a16, &map_a, bar, 0, 0);
+        tma_load_2d(a8, &map_a, bar, 0, 128);
+        tma_load_2d(b16, &map_b, bar, 0, 0);
+        tma_load_2d(b8, &map_b, bar, 0, 64);
+    }
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        const uint32_t idesc16 = make_idesc_f16(128, 64);
+        const uint32_t idesc8 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // E4M3 x E4M3 -> F32
+        if (mode >= 1) {
+            for (int k = 0; k < 4; ++k) umma_f8(tmem, make_smem_desc(a8 + k * 32, 128), make_smem_desc(b8 + k * 32, 128), idesc8, k != 0);
+            if (mode == 1) {      // main terms on top, first one rescales the correction sum
+                umma_f16_scaled(tmem, make_smem_desc(a16, 128), make_smem_desc(b16, 128), idesc16);
+                for (int k = 1; k < 4; ++k) umma_bf16(tmem, make_smem_desc(a16 + k * 32, 128), make_smem_desc(b16 + k * 32, 128), idesc16, 1);
+            }
+        } else {
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem, make_smem_desc(a16 + k * 32, 128), make_smem_desc(b16 + k * 32, 128), idesc16, k != 0);
+        }
+        umma_commit(bar2);
+    }
+    mbar_wait(bar2, 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) out[(size_t)r * 64 + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem, 64);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+static uint8_t e4m3(float v, float* back) {
+    __nv_fp8_e4m3 q(v);
+    *back = (float)q;
+    uint8_t u; memcpy(&u, &q, 1);
+    return u;
+}
+
+int main() {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    CK(cudaFree(0));
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    EncodeTiledFn enc = (EncodeTiledFn)fn;
+    const int SA = 11, SW1 = 4, SW2 = 15;            // a_lo * 2^11, w_hi * 2^4, w_lo * 2^15  (11 + 4 = 0 + 15)
+    for (float a_scale : {1.f, 8.f, 0.05f}) {
+        std::vector<float> A(128 * 64), B(64 * 64);
+        srand(7);
+        auto rnd = [] { return (float)rand() / RAND_MAX * 2.f - 1.f; };
+        for (auto& v : A) v = fabsf(rnd()) * a_scale * (rand() % 8 == 0 ? 0.01f : 1.f);
+        for (auto& v : B) v = rnd() * 0.05f;
+        // byte images: rows of 128 bytes.  A: rows 0..127 fp16 hi, rows 128..255 the e4m3 plane [lo8 (64) | hi8 (64)]
+        std::vector<uint8_t> abytes(256 * 128), bbytes(128 * 128);
+        std::vector<double> Aeff_main(128 * 64), Beff_main(64 * 64), A8lo(128 * 64), A8hi(128 * 64), B8hi(64 * 64), B8lo(64 * 64);
+        for (int i = 0; i < 128 * 64; ++i) {
+            const int r = i / 64, c = i % 64;
+            const __half h = __float2half_rn(A[i]);
+            memcpy(&abytes[r * 128 + 2 * c], &h, 2);
+            const float hf = __half2float(h);
+            Aeff_main[i] = hf;
+            float b1, b2;
+            abytes[(128 + r) * 128 + c] = e4m3(ldexpf(A[i] - hf, SA), &b1);
+            abytes[(128 + r) * 128 + 64 + c] = e4m3(hf, &b2);
+            A8lo[i] = b1; A8hi[i] = b2;
+        }
+        for (int i = 0; i < 64 * 64; ++i) {
+            const int r = i / 64, c = i % 64;
+            const __half h = __float2half_rn(B[i]);
+            memcpy(&bbytes[r * 128 + 2 * c], &h, 2);
+            const float hf = __half2float(h);
+            Beff_main[i] = hf;
+            float b1, b2;
+            bbytes[(64 + r) * 128 + c] = e4m3(ldexpf(hf, SW1), &b1);
+            bbytes[(64 + r) * 128 + 64 + c] = e4m3(ldexpf(B[i] - hf, SW2), &b2);
+            B8hi[i] = b1; B8lo[i] = b2;
+        }
+        uint8_t *da, *db; CK(cudaMalloc(&da, abytes.size())); CK(cudaMalloc(&db, bbytes.size()));
+        CK(cudaMemcpy(da, abytes.data(), abytes.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(db, bbytes.data(), bbytes.size(), cudaMemcpyHostToDevice));
+        CUtensorMap ma, mb;
+        { cuuint64_t d[2] = {128, 256}; cuuint64_t s[1] = {128}; cuuint32_t b[2] = {128, 128}; cuuint32_t e[2] = {1, 1};
+          CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, da, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE); if (r) { printf("encode a failed %d\n", (int)r); return 1; } }
+        { cuuint64_t d[2] = {128, 128}; cuuint64_t s[1] = {128}; cuuint32_t b[2] = {128, 64}; cuuint32_t e[2] = {1, 1};
+          CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, db, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE); if (r) { printf("encode b failed %d\n", (int)r); return 1; } }
+        float* dout; CK(cudaMalloc(&dout, 128 * 64 * 4));
+        const int smem = 49152 + 64 + 1024;
+        CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        for (int mode : {0, 2, 1}) {
+            probe_kernel<<<1, 128, smem>>>(ma, mb, mode, dout);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("mode %d: kernel failed: %s\n", mode, cudaGetErrorString(e)); return 1; }
+            std::vector<float> D(128 * 64);
+            CK(cudaMemcpy(D.data(), dout, D.size() * 4, cudaMemcpyDeviceToHost));
+            double max_model = 0, err_true = 0, ref2 = 0;
+            for (int m = 0; m < 128; ++m)
+                for (int n = 0; n < 64; ++n) {
+                    double main = 0, corr = 0, tru = 0;
+                    for (int k = 0; k < 64; ++k) {
+                        main += Aeff_main[m * 64 + k] * Beff_main[n * 64 + k];
+                        corr += A8lo[m * 64 + k] * B8hi[n * 64 + k] + A8hi[m * 64 + k] * B8lo[n * 64 + k];
+                        tru += (double)A[m * 64 + k] * (double)B[n * 64 + k];
+                    }
+                    const double model = mode == 0 ? main : mode == 2 ? corr : main + ldexp(corr, -15);
+                    max_model = fmax(max_model, fabs(D[m * 64 + n] - model));
+                    err_true += (D[m * 64 + n] - tru) * (D[m * 64 + n] - tru); ref2 += tru * tru;
+                }
+            printf("a_scale %-5g mode %d (%s): max |D - model| %.3e ; rel rms error vs FP32-operand product %.3e\n", a_scale, mode,
+                   mode == 0 ? "fp16 main only" : mode == 2 ? "fp8 correction only, unscaled" : "fp8 correction, then fp16 main with scale-input-d 15",
+                   max_model, mode == 2 ? NAN : sqrt(err_true / ref2));
+        }
+        cudaFree(da); cudaFree(db); cudaFree(dout);
+    }
+    return 0;
+}
