@@ -27,14 +27,14 @@ __device__ __forceinline__ void umma_f16_scaled(uint32_t tmem_d, uint64_t adesc,
 
 // global: A16 [128][64] fp16 | A8 [128][128] e4m3 ; B16 [64][64] fp16 | B8 [64][128] e4m3  (all rows 128 bytes, SWIZZLE_128B)
 __global__ void __launch_bounds__(128, 1)
-probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int mode, float* out) {
+probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int mode, float* out, const uint32_t* a_img) {
     extern __shared__ uint8_t raw[];
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
     const uint32_t a16 = base, a8 = base + 16384, b16 = base + 32768, b8 = base + 32768 + 8192;
     const uint32_t bar = base + 49152, bar2 = bar + 8, slot = bar + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); fence_barrier_init(); }
-    if (warp == 1) { tmem_alloc(slot, 64); tmem_relinquish(); }
+    if (warp == 1) { tmem_alloc(slot, 256); tmem_relinquish(); }
     tc_fence_before(); __syncthreads(); tc_fence_after();
     uint32_t tmem; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
     if (threadIdx.x == 0) {
@@ -46,6 +46,27 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
     mbar_wait(bar, 0);
     tc_fence_after();
+    if (mode == 3) {
+        // A operands in tensor memory: row r = this thread's lane; columns 64..95 = the FP16 row (2 values per column), 96..127 = the
+        // e4m3 row (4 values per column) -- does kind::f8f6f4 read 4 consecutive K per 32-bit column?
+        const int r = warp * 32 + lane;
+        uint32_t w16[32], w8[32];
+        for (int i = 0; i < 32; ++i) { w16[i] = a_img[(size_t)r * 32 + i]; w8[i] = a_img[(size_t)(128 + r) * 32 + i]; }
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 64, w16);
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 96, w8);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (threadIdx.x == 0) {
+            const uint32_t hi128 = (uint32_t)((8 * 128) >> 4) | (1u << 14) | (2u << 29);
+            auto LO = [](uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); };
+            for (int k = 0; k < 4; ++k) umma_ts_f8_lohi(tmem, tmem + 96 + 8 * k, LO(b8) + 2 * k, hi128, make_idesc_e4m3(128, 64), k != 0);
+            umma_ts_lohi_rescale(tmem, tmem + 64, LO(b16), hi128, make_idesc_f16(128, 64));
+            for (int k = 1; k < 4; ++k) umma_ts_lohi(tmem, tmem + 64 + 8 * k, LO(b16) + 2 * k, hi128, make_idesc_f16(128, 64), 1);
+            umma_commit(bar2);
+        }
+    } else
     if (threadIdx.x == 0) {
         const uint32_t idesc16 = make_idesc_f16(128, 64);
         const uint32_t idesc8 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // E4M3 x E4M3 -> F32
@@ -70,7 +91,7 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         for (int i = 0; i < 16; ++i) out[(size_t)r * 64 + c0 + i] = __uint_as_float(v[i]);
     }
     tc_fence_before(); __syncthreads(); tc_fence_after();
-    if (warp == 1) tmem_dealloc(tmem, 64);
+    if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -132,8 +153,8 @@ int main() {
         float* dout; CK(cudaMalloc(&dout, 128 * 64 * 4));
         const int smem = 49152 + 64 + 1024;
         CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        for (int mode : {0, 2, 1}) {
-            probe_kernel<<<1, 128, smem>>>(ma, mb, mode, dout);
+        for (int mode : {0, 2, 1, 3}) {
+            probe_kernel<<<1, 128, smem>>>(ma, mb, mode, dout, (const uint32_t*)da);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("mode %d: kernel failed: %s\n", mode, cudaGetErrorString(e)); return 1; }
             std::vector<float> D(128 * 64);
@@ -152,7 +173,7 @@ int main() {
                     err_true += (D[m * 64 + n] - tru) * (D[m * 64 + n] - tru); ref2 += tru * tru;
                 }
             printf("a_scale %-5g mode %d (%s): max |D - model| %.3e ; rel rms error vs FP32-operand product %.3e\n", a_scale, mode,
-                   mode == 0 ? "fp16 main only" : mode == 2 ? "fp8 correction only, unscaled" : "fp8 correction, then fp16 main with scale-input-d 15",
+                   mode == 0 ? "fp16 main only" : mode == 2 ? "fp8 correction only, unscaled" : mode == 1 ? "fp8 correction, then fp16 main with scale-input-d 15" : "same with both A operands in tensor memory",
                    max_model, mode == 2 ? NAN : sqrt(err_true / ref2));
         }
         cudaFree(da); cudaFree(db); cudaFree(dout);

@@ -69,6 +69,13 @@ extern "C" {
  * on random-init weights; plain BF16 / FP16 do not. */
 #define UKBB_MODE_BF16X3  4
 #define UKBB_MODE_FP16X3  5
+/* The "2x" scheme: FP16 pieces as FP16X3, but BOTH correction products of a K step are ONE FP8 (E4M3) tensor-core instruction:
+ *   a.w  ~=  a_hi.w_hi  +  2^-15 [e4m3(a_lo 2^11) | e4m3(a_hi)] . [e4m3(w_hi 2^4) | e4m3(w_lo 2^15)]
+ * (K = 32 FP8 elements occupy the 32 bytes of an FP16 K = 16 step, so tensors keep the two-plane layout; the 2^-15 is the
+ * scale-input-d of the first FP16 instruction).  Two instructions per K step instead of three; the corrections carry 4 significant
+ * bits, so the product error is ~2^-16.7 relative (FP16: 2^-11.8, FP16X3: 2^-22): ~28x tighter than FP16 -- measured by
+ * experiments/x2f8_probe.cu -- and enough for the label tolerance above, not for the 1e-4 logits tolerance of FP32 mode. */
+#define UKBB_MODE_FP16X2  6
 
 #define UKBB_N_CONV 21      /* 13 encoder 3x3 + 5 same_dim 1x1 + fc0 + fc1 + logits */
 #define UKBB_MAX_CLASS 8

@@ -207,7 +207,7 @@ def test_run_workers_drains_pipes_concurrently(monkeypatch, capsys):
 
 
 def test_default_mode_is_the_compliant_one():
-    assert deploy.parse_flags([]).mode == "fp16x3"
+    assert deploy.parse_flags([]).mode == "fp16x2"
     assert deploy.parse_flags(["--mode", "bf16"]).mode == "bf16"
     with pytest.raises(SystemExit):
         deploy.parse_flags(["--mode", "int8"])

@@ -37,7 +37,7 @@ def test_cli_process_seq(tmp_path, seq, shape, n_class, mode):
         else:
             nifti.save(img, str(d / (seq + ".nii.gz")))
     cmd = [sys.executable, os.path.join(ROOT, "common", "deploy_network.py"), "--seq_name", seq, "--data_dir", str(data),
-           "--model_path", str(tmp_path / "model" / ("FCN_" + seq))] + (["--mode", mode] if mode else [])      # None = the default mode (fp16x3)
+           "--model_path", str(tmp_path / "model" / ("FCN_" + seq))] + (["--mode", mode] if mode else [])      # None = the default mode (fp16x2)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Start deployment on the data set ..." in r.stdout and "for processing %d subjects" % NS in r.stdout

@@ -19,6 +19,7 @@ MODE_BF16 = 2
 MODE_FP16 = 3
 MODE_BF16X3 = 4     # split operands (hi + lo 16-bit pairs, three tcgen05.mma per K step): 16-bit significand
 MODE_FP16X3 = 5     # same with FP16 pieces: 22-bit significand -- the default tensor-core mode
+MODE_FP16X2 = 6     # FP16 pieces, both correction products as one FP8 (E4M3) instruction: two tcgen05.mma per K step
 N_CONV = 21
 MAX_CLASS = 8
 

@@ -195,7 +195,8 @@ int ukbb_fcn_create(const ukbb_fcn_weights* w, int n_class, int device, int mode
     *out = nullptr;
     UKBB_REQUIRE(w->n_conv == UKBB_N_CONV && w->conv, "create: expected %d conv layers, got %d", UKBB_N_CONV, w->n_conv);
     UKBB_REQUIRE(n_class >= 2 && n_class <= UKBB_MAX_CLASS, "create: n_class=%d not in [2,%d]", n_class, UKBB_MAX_CLASS);
-    UKBB_REQUIRE(mode == UKBB_MODE_FP32 || mode == UKBB_MODE_BF16 || mode == UKBB_MODE_FP16 || mode == UKBB_MODE_BF16X3 || mode == UKBB_MODE_FP16X3,
+    UKBB_REQUIRE(mode == UKBB_MODE_FP32 || mode == UKBB_MODE_BF16 || mode == UKBB_MODE_FP16 || mode == UKBB_MODE_BF16X3 || mode == UKBB_MODE_FP16X3 ||
+                 mode == UKBB_MODE_FP16X2,
                  "create: unknown mode %d", mode);
     for (int i = 0; i < UKBB_N_CONV; ++i) {
         int ks, cin, cout, stride;

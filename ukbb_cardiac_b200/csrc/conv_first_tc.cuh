@@ -52,8 +52,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint3
 }
 }  // namespace tc
 
-template <bool SPLIT = false>
+template <bool SPLIT = false, bool F8 = false>
 struct ConvFirstTcCfg {
+    static constexpr bool MERGE = SPLIT && !F8;                 // x3: N = 128 merge of the hi.hi / hi.lo products; x2 (F8): FP8 correction pass
     static constexpr int PU = 10, PR = 18, J = 6, N = 64;
     static constexpr int GROUPS = PU * PR;                      // 180 patch group rows per tile
     static constexpr int BUILDERS = 6;                          // builder warps with work (8 launched: TMEM lane quarters)
@@ -76,8 +77,8 @@ struct ConvFirstTcCfg {
     // TMEM columns.  plain: conv0_1 accumulators 2 x 64 | D0 2 stages x 2 blocks x 64 | A0 2 stages x 2 blocks x 32.
     // SPLIT: conv0_1 accumulators 2 x 128 (columns [0, 64) = hi.hi + lo.hi, [64, 128) = hi.lo: the N = 128 merge of conv_group.cuh) |
     //        D0 ONE stage x 2 blocks x 64 (the finisher loads all 64 columns and releases it before converting) | A0 as before.
-    static constexpr int ACC_COLS = SPLIT ? 128 : 64;
-    static constexpr int D0_STAGES = SPLIT ? 1 : 2;
+    static constexpr int ACC_COLS = MERGE ? 128 : 64;
+    static constexpr int D0_STAGES = MERGE ? 1 : 2;
     static constexpr int COL_ACC = 0, COL_D0 = 2 * ACC_COLS, COL_A0 = 384;
     static_assert(COL_D0 + D0_STAGES * 2 * 64 <= COL_A0, "TMEM budget");
     static constexpr int SMEM_BYTES = A_STAGES * PATCH_BYTES + B_BYTES + B0_BYTES + 2 * OUT_BYTES + IMG_STAGES * IMG_BYTES + 256 /*barriers*/ +
@@ -85,13 +86,14 @@ struct ConvFirstTcCfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <bool F16, bool SPLIT = false>
+template <bool F16, bool SPLIT = false, bool F8 = false>
 __global__ void __launch_bounds__(ConvFirstTcCfg<>::THREADS, 1)
 conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_out,
                      const __grid_constant__ ConvFirstParams p) {
     using namespace tc;
-    using Cfg = ConvFirstTcCfg<SPLIT>;
+    using Cfg = ConvFirstTcCfg<SPLIT, F8>;
+    constexpr bool MERGE = Cfg::MERGE;
     constexpr int AST = Cfg::A_STAGES, IST = Cfg::IMG_STAGES, J = Cfg::J, PU = Cfg::PU, N = Cfg::N;
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
@@ -148,7 +150,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) {
                 // global: hi tiles, then lo tiles.  Shared (SPLIT): tile t = [hi 64 rows | lo 64 rows], one N = 128 B operand
                 const int tt = t % Cfg::NB_TILES, pl = t / Cfg::NB_TILES;
-                tma_load_2d(b_base + (SPLIT ? tt * 2 * Cfg::B_TILE + pl * Cfg::B_TILE : t * Cfg::B_TILE), &map_b, wfull, 0, t * N);
+                tma_load_2d(b_base + (MERGE ? tt * 2 * Cfg::B_TILE + pl * Cfg::B_TILE : t * Cfg::B_TILE), &map_b, wfull, 0, t * N);
             }
             tma_load_2d(b0_base, &map_b0, wfull, 0, 0);
             griddep_wait();
@@ -168,7 +170,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
         // ===================== MMA issuer (conv0_1, as conv_group<16, 16, 1>) =====================
         const bool leader = elect_one();
         const uint32_t idesc = F16 ? make_idesc_f16(128, N) : make_idesc_bf16(128, N);
-        const uint32_t idesc2 = F16 ? make_idesc_f16(128, 2 * N) : make_idesc_bf16(128, 2 * N);    // SPLIT: A_hi . [w_hi ; w_lo]^T
+        const uint32_t idesc2 = F16 ? make_idesc_f16(128, 2 * N) : make_idesc_bf16(128, 2 * N);    // x3: A_hi . [w_hi ; w_lo]^T
+        const uint32_t idesc8 = make_idesc_e4m3(128, N);                                           // x2: FP8 correction pass
         constexpr uint32_t a_hi = (uint32_t)((PU * 128) >> 4) | (1u << 14) | (2u << 29);       // 8-row groups one patch row apart, 128 B swizzle
         constexpr uint32_t b_hi = (uint32_t)((8 * 32) >> 4) | (1u << 14) | (6u << 29);         // weights: 32-byte rows, 32 B swizzle
         const uint32_t b_lo = ((b_base & 0x3FFFF) >> 4) | (1u << 16);
@@ -184,6 +187,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             const uint32_t a_lo = (((smem_base + as * Cfg::PATCH_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
             if (leader) {
 #pragma unroll
+                for (int pass = F8 ? 0 : 1; pass < 2; ++pass)                    // x2: pass 0 = FP8 corrections, pass 1 = FP16 main term
+#pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
@@ -191,8 +196,12 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                         const int ro = jj < 0 ? -1 : jj / 4;
                         const int sub = jj - ro * 4;
                         const int arow = ky * PU + 1 + ro;
-                        const uint32_t ao = (uint32_t)((arow * 128 + sub * 32) >> 4), bo = (uint32_t)(((ky * J + j) * (SPLIT ? 2 : 1) * Cfg::B_TILE) >> 4);
-                        if (SPLIT) {
+                        const uint32_t ao = (uint32_t)((arow * 128 + sub * 32) >> 4), bo = (uint32_t)(((ky * J + j) * (MERGE ? 2 : 1) * Cfg::B_TILE) >> 4);
+                        if (F8) {
+                            if (pass == 0) umma_f8_lohi(d, a_lo + (Cfg::PLANE_BYTES >> 4) + ao, a_hi, b_lo + (Cfg::B_SET >> 4) + bo, b_hi, idesc8, (ky | j) != 0 ? 1u : 0u);
+                            else if ((ky | j) == 0) umma_f16_lohi_rescale(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc);
+                            else umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, 1u);
+                        } else if (SPLIT) {
                             umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc2, (ky | j) != 0 ? 1u : 0u);                    // hi . [hi ; lo]
                             umma_bf16_lohi(d, a_lo + (Cfg::PLANE_BYTES >> 4) + ao, a_hi, b_lo + bo, b_hi, idesc, 1u);                // lo . hi
                         } else {
@@ -217,8 +226,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
         for (int i = 0; i < my_tiles; ++i) {
             const int s = i & 1;
             const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-            const int ds = SPLIT ? 0 : s;                                            // D0 stage (SPLIT: one stage, phase = tile parity)
-            const uint32_t dph = SPLIT ? ((uint32_t)i & 1u) : ph;
+            const int ds = MERGE ? 0 : s;                                            // D0 stage (x3: one stage, phase = tile parity)
+            const uint32_t dph = MERGE ? ((uint32_t)i & 1u) : ph;
             mbar_wait(BAR(D0_EMPTY + ds), dph ^ 1);
             mbar_wait(BAR(A0_FULL + s), ph);
             tc_fence_after();
@@ -288,7 +297,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             if (i + 1 < my_tiles) build(i + 1);
             // ---- finish tile i: D0 -> shift + ReLU -> 16 bit -> the 128-byte patch row of conv0_1
             const int s = i & 1, as = i % AST;
-            if (!SPLIT) {
+            if (!MERGE) {
                 mbar_wait(BAR(D0_FULL + s), ((uint32_t)i >> 1) & 1u);
                 tc_fence_after();
             }
@@ -299,14 +308,17 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                 // D0 has ONE stage here: load all 64 accumulator columns, release it, then convert (one pixel = 16 columns at a time)
                 // into the hi and lo rows of the patch, two swizzled STS.128 each
                 uint32_t d[64];
-                mbar_wait(BAR(D0_FULL), (uint32_t)i & 1u);
-                tc_fence_after();
-                tmem_ld32(lane_base + Cfg::COL_D0 + m * 64, d);
-                tmem_ld32(lane_base + Cfg::COL_D0 + m * 64 + 32, d + 32);
+                if (MERGE) {
+                    mbar_wait(BAR(D0_FULL), (uint32_t)i & 1u);
+                    tc_fence_after();
+                }
+                const int dstage = MERGE ? 0 : s;
+                tmem_ld32(lane_base + Cfg::COL_D0 + (dstage * 2 + m) * 64, d);
+                tmem_ld32(lane_base + Cfg::COL_D0 + (dstage * 2 + m) * 64 + 32, d + 32);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(D0_EMPTY));
+                if (lane == 0) mbar_arrive(BAR(D0_EMPTY + dstage));
                 mbar_wait(a_empty(as), ((uint32_t)(i / AST) & 1u) ^ 1u);
                 const uint32_t row = smem_base + as * Cfg::PATCH_BYTES + (uint32_t)g * 128u;
 #pragma unroll
@@ -314,9 +326,10 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                     uint32_t oh[8], ol[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        add_relu_split<F16>(d[16 * qt + 2 * c], d[16 * qt + 2 * c + 1], p.shift0[2 * c], p.shift0[2 * c + 1], oh[c], ol[c]);
+                        add_relu_split<F16, F8>(d[16 * qt + 2 * c], d[16 * qt + 2 * c + 1], p.shift0[2 * c], p.shift0[2 * c + 1], oh[c], ol[c]);
                         if (!inside) { oh[c] = 0u; ol[c] = 0u; }
                     }
+                    if (F8) x2_regroup(ol);
                     if (active) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
@@ -384,22 +397,25 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                 for (int c8 = 0; c8 < 4; ++c8) {
                     uint32_t v[16], v2[16], oh[8], ol[8];
                     tmem_ld16(taddr + 16 * c8, v);
-                    tmem_ld16(taddr + 64 + 16 * c8, v2);
+                    if (MERGE) tmem_ld16(taddr + 64 + 16 * c8, v2);
                     tmem_ld_wait();
                     if (c8 == 3) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty(acc));
                     }
+                    if (MERGE) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+                        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+                    }
 #pragma unroll
                     for (int c = 0; c < 16; c += 4) {
                         const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
                         const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
-                        bn_relu_split<F16>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
-                        bn_relu_split<F16>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1], ol[c / 2 + 1]);
+                        bn_relu_split<F16, F8>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
+                        bn_relu_split<F16, F8>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1], ol[c / 2 + 1]);
                     }
+                    if (F8) x2_regroup(ol);
                     if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
                 }
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }

@@ -46,8 +46,12 @@ struct ConvGroupParams {
 // adds into columns [0, 64).  The epilogue sums the two column blocks.  112 instead of 144 port cycles per K-slice.
 // TROWS: output rows per tile (<= 16; the UMMA still has M = 128 = 16 rows x 8 groups, rows >= TROWS are idle): the 64 -> 64 split
 // instance holds 144 KB of weights and fits two (hi, lo) patch stages only with 14-row tiles.
-template <int CC, int COUT, int STRIDE, bool SPLIT = false>
+// F8 (x2 scheme, tc_common.cuh): the lo planes hold FP8 correction operands; per K-slice ONE kind::f8f6f4 UMMA (A_lo8 . B_lo8) replaces the
+// two correction products, all of them are issued before the FP16 pass whose first instruction rescales the accumulator.
+template <int CC, int COUT, int STRIDE, bool SPLIT = false, bool F8 = false>
 struct ConvGroupCfg {
+    static_assert(!F8 || SPLIT, "the FP8 correction scheme is a split-operand scheme");
+    static constexpr bool MERGE = SPLIT && !F8;                // x3: [w_hi ; w_lo] tiles, N = 128 UMMAs, two accumulator column blocks
     static constexpr int G = 64 / CC;                          // input pixels per 128-byte row
     static constexpr int GOUT = STRIDE == 1 ? G : G / 2;       // output pixels per UMMA row
     static constexpr int N = GOUT * COUT;
@@ -68,7 +72,7 @@ struct ConvGroupCfg {
     static constexpr int A_MAX = ((SPLIT ? 224 : 200) * 1024 - B_BYTES - 2 * OUT_BYTES) / A_STAGE_BYTES;
     static constexpr int A_STAGES = A_MAX > 4 ? 4 : A_MAX;
     static constexpr int ACC_STAGES = 2;
-    static constexpr int ACC_COLS = SPLIT ? 2 * N : N;         // SPLIT: columns [0, N) = hi.hi + lo.hi, [N, 2N) = hi.lo
+    static constexpr int ACC_COLS = MERGE ? 2 * N : N;         // x3: columns [0, N) = hi.hi + lo.hi, [N, 2N) = hi.lo
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_BYTES + 2 * OUT_BYTES + 1024 + 256 + 2 * N * 4;
     static_assert(N == 64, "pixel-group kernel is built for N = Gout * Cout = 64");
@@ -105,7 +109,7 @@ __device__ __forceinline__ uint32_t bn_relu_pack(uint32_t a0, uint32_t a1, float
     return r;
 }
 // same arithmetic, but the result is split into 16-bit hi and lo pieces (x3 modes): v = max(a * sc + sh, 0) ~ hi + lo
-template <bool F16>
+template <bool F16, bool F8 = false>
 __device__ __forceinline__ void bn_relu_split(uint32_t a0, uint32_t a1, float2 sc, float2 sh, uint32_t& hi, uint32_t& lo) {
     uint64_t a, b, c, d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
@@ -114,7 +118,7 @@ __device__ __forceinline__ void bn_relu_split(uint32_t a0, uint32_t a1, float2 s
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     float x0, x1;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
-    split_pack<F16>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
+    split_pack<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
 }
 // one 256-bit global store (STG.256): a full 32-byte sector per thread
 __device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
@@ -150,12 +154,13 @@ struct TileWalk {
     }
 };
 
-template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT = false>
+template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT = false, bool F8 = false>
 __global__ void __launch_bounds__(256, 1)
 conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const ConvGroupParams p) {
     using namespace tc;
-    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT>;
+    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT, F8>;
+    constexpr bool MERGE = Cfg::MERGE;
     constexpr int AST = Cfg::A_STAGES, G = Cfg::G, J = Cfg::J, KS = Cfg::KS, PU = Cfg::PU, N = Cfg::N, TROWS = Cfg::TROWS;
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
@@ -201,7 +206,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) {
                 // global: hi tiles, then lo tiles.  Shared (SPLIT): tile t = [hi 64 rows | lo 64 rows], one N = 128 B operand
                 const int tt = t % Cfg::NB_TILES, pl = t / Cfg::NB_TILES;
-                tma_load_2d(b_base + (SPLIT ? tt * 2 * Cfg::B_TILE + pl * Cfg::B_TILE : t * Cfg::B_TILE), &map_b, wfull, 0, t * N);
+                tma_load_2d(b_base + (MERGE ? tt * 2 * Cfg::B_TILE + pl * Cfg::B_TILE : t * Cfg::B_TILE), &map_b, wfull, 0, t * N);
             }
             griddep_wait();
             TileWalk w;
@@ -223,7 +228,8 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
         const bool leader = elect_one();
         const uint32_t idesc = F16 ? make_idesc_f16(128, N) : make_idesc_bf16(128, N);
-        const uint32_t idesc2 = F16 ? make_idesc_f16(128, 2 * N) : make_idesc_bf16(128, 2 * N);       // SPLIT: A_hi . [w_hi ; w_lo]^T
+        const uint32_t idesc2 = F16 ? make_idesc_f16(128, 2 * N) : make_idesc_bf16(128, 2 * N);       // x3: A_hi . [w_hi ; w_lo]^T
+        const uint32_t idesc8 = make_idesc_e4m3(128, N);                                              // x2: FP8 correction pass
         constexpr uint32_t blayout = Cfg::B_ROW == 128 ? 2u : Cfg::B_ROW == 64 ? 4u : 6u;
         constexpr uint32_t a_hi = (uint32_t)(((STRIDE == 1 ? PU : 2 * PU) * 128) >> 4) | (1u << 14) | (2u << 29);
         constexpr uint32_t b_hi = (uint32_t)((8 * Cfg::B_ROW) >> 4) | (1u << 14) | (blayout << 29);
@@ -240,6 +246,8 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t a_lo = (((smem_base + as * Cfg::A_STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
             if (leader) {
 #pragma unroll
+                for (int pass = F8 ? 0 : 1; pass < 2; ++pass)            // x2: pass 0 = FP8 corrections, pass 1 = FP16 main term
+#pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
@@ -251,8 +259,12 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
                             const uint32_t ao = (uint32_t)((arow * 128 + sub * CC * 2 + ks * 32) >> 4);
-                            const uint32_t bo = (uint32_t)(((ky * J + j) * (SPLIT ? 2 : 1) * Cfg::B_TILE + ks * 32) >> 4);
-                            if (SPLIT) {
+                            const uint32_t bo = (uint32_t)(((ky * J + j) * (MERGE ? 2 : 1) * Cfg::B_TILE + ks * 32) >> 4);
+                            if (F8) {
+                                if (pass == 0) umma_f8_lohi(d, a_lo + (Cfg::PATCH_BYTES >> 4) + ao, a_hi, b_lo + (Cfg::B_SET >> 4) + bo, b_hi, idesc8, (ky | j | ks) != 0 ? 1u : 0u);
+                                else if ((ky | j | ks) == 0) umma_f16_lohi_rescale(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc);
+                                else umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, 1u);
+                            } else if (SPLIT) {
                                 umma_bf16_lohi(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc2, (ky | j | ks) != 0 ? 1u : 0u);           // hi . [hi ; lo]
                                 umma_bf16_lohi(d, a_lo + (Cfg::PATCH_BYTES >> 4) + ao, a_hi, b_lo + bo, b_hi, idesc, 1u);            // lo . hi
                             } else {
@@ -290,22 +302,25 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int c8 = 0; c8 < 4; ++c8) {
                     uint32_t v[16], v2[16], oh[8], ol[8];
                     tmem_ld16(taddr + 16 * c8, v);
-                    tmem_ld16(taddr + 64 + 16 * c8, v2);
+                    if (MERGE) tmem_ld16(taddr + 64 + 16 * c8, v2);
                     tmem_ld_wait();
                     if (c8 == 3) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty(acc));     // accumulator is in registers: release it to the MMA warp
                     }
+                    if (MERGE) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+                        for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+                    }
 #pragma unroll
                     for (int c = 0; c < 16; c += 4) {
                         const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
                         const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
-                        bn_relu_split<F16>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
-                        bn_relu_split<F16>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1], ol[c / 2 + 1]);
+                        bn_relu_split<F16, F8>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
+                        bn_relu_split<F16, F8>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1], ol[c / 2 + 1]);
                     }
+                    if (F8) x2_regroup(ol);
                     if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
                 }
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }

@@ -36,12 +36,16 @@ struct ConvHaloParams {
 // SPLIT (x3 modes, streamed weights only): a patch stage holds the hi and the lo patch of a chunk, and the weight stream alternates
 // hi / lo tiles: per (chunk, tap) the issuer takes the hi tile (UMMAs A_hi.B_hi and A_lo.B_hi), then the lo tile (A_hi.B_lo).  The
 // split instances use 32-channel chunks (64-byte rows) so that two (hi, lo) patch stages and an 8-deep weight ring still fit.
-template <int CC, int COUT, bool RESIDENT, int NKB /* 9 * chunks when RESIDENT */, bool SPLIT = false>
+// F8 (x2 scheme, tc_common.cuh): the chunks of a tile are walked TWICE -- lo planes first (patch + weight tiles holding FP8 correction
+// operands, kind::f8f6f4), then the hi planes (kind::f16; the first instruction of each sub-tile rescales its accumulator) -- so a patch stage
+// holds one plane and the weight stream is one tile per (pass, chunk, tap).
+template <int CC, int COUT, bool RESIDENT, int NKB /* 9 * chunks when RESIDENT */, bool SPLIT = false, bool F8 = false>
 struct ConvHaloCfg {
     static_assert(!SPLIT || !RESIDENT, "the split variant streams its weights");
+    static_assert(!F8 || SPLIT, "the FP8 correction scheme is a split-operand scheme");
     static constexpr int RB = CC * 2;                                   // bytes per patch row (pixel)
     static constexpr int PLANE_BYTES = (324 * RB + 1023) / 1024 * 1024;
-    static constexpr int PATCH_BYTES = (SPLIT ? 2 : 1) * PLANE_BYTES;
+    static constexpr int PATCH_BYTES = ((SPLIT && !F8) ? 2 : 1) * PLANE_BYTES;
     static constexpr int B_TILE = (COUT * RB + 1023) / 1024 * 1024;
     // streamed weights: the ring must cover the ~2000-cycle latency of an L2 fetch -- with four 16 KB stages (512 cycles of UMMAs
     // each) the tensor pipe waited for weights half of the time (7350 cycles per chunk for 3456 cycles of UMMAs); two patch stages
@@ -66,12 +70,14 @@ struct ConvHaloCfg {
 // multicast that lands at the same shared-memory offset in both CTAs and signals both b_full barriers -- and a ring slot is refilled
 // only after BOTH tensor pipes have consumed it (tcgen05.commit multicast on both b_empty barriers, count 2).  The level-3/4 layers
 // stream 0.29 / 1.18 MB of weights per 16x16-pixel tile and ran at the L2 roofline (6.7 TB/s of L2 reads).
-template <int CC, int COUT, bool RESIDENT, int NKB, bool F16, bool CL = false, bool SPLIT = false>
+template <int CC, int COUT, bool RESIDENT, int NKB, bool F16, bool CL = false, bool SPLIT = false, bool F8 = false>
 __global__ void __launch_bounds__(256, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const ConvHaloParams p) {
     using namespace tc;
-    using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB, SPLIT>;
+    using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB, SPLIT, F8>;
+    constexpr bool X3 = SPLIT && !F8;
+    const int n_chunk_steps = F8 ? 2 * p.chunks : p.chunks;     // x2: [0, chunks) = lo planes, [chunks, 2 chunks) = hi planes
     constexpr int RB = Cfg::RB, AST = Cfg::A_STAGES, BST = Cfg::B_TILES, ACC = Cfg::ACC_STAGES;
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
@@ -142,15 +148,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int tile = tile_first; tile < tile_end; tile += tile_step) {
                 const int txi = tile / tiles_per_tx, t2 = tile - txi * tiles_per_tx;
                 const int n = t2 / p.tiles_y, y0 = (t2 - n * p.tiles_y) * 16, x0 = txi * 16;
-                for (int ch = 0; ch < p.chunks; ++ch) {
+                for (int cs = 0; cs < n_chunk_steps; ++cs) {
+                    const int ch = (F8 && cs >= p.chunks) ? cs - p.chunks : cs;
+                    const bool lo_pass = F8 && cs < p.chunks;
                     mbar_wait(a_empty(as), aph ^ 1);
-                    mbar_arrive_expect_tx(a_full(as), (SPLIT ? 2 : 1) * 324 * RB);
-                    tma_load_4d(smem_base + as * Cfg::PATCH_BYTES, &map_a, a_full(as), ch * CC, x0 - 1, y0 - 1, n);
-                    if (SPLIT) tma_load_4d(smem_base + as * Cfg::PATCH_BYTES + Cfg::PLANE_BYTES, &map_a, a_full(as), ch * CC, x0 - 1, y0 - 1, p.lo_n + n);
+                    mbar_arrive_expect_tx(a_full(as), (X3 ? 2 : 1) * 324 * RB);
+                    tma_load_4d(smem_base + as * Cfg::PATCH_BYTES, &map_a, a_full(as), ch * CC, x0 - 1, y0 - 1, (lo_pass ? p.lo_n : 0) + n);
+                    if (X3) tma_load_4d(smem_base + as * Cfg::PATCH_BYTES + Cfg::PLANE_BYTES, &map_a, a_full(as), ch * CC, x0 - 1, y0 - 1, p.lo_n + n);
                     if (++as == AST) { as = 0; aph ^= 1; }
                     if (!RESIDENT) {
-                        for (int tap = 0; tap < (SPLIT ? 18 : 9); ++tap) {      // split: (tap, hi), (tap, lo), ... ; lo tiles are rows [COUT, 2 COUT) of the weight map
-                            const int tp = SPLIT ? tap >> 1 : tap, wrow = SPLIT ? (tap & 1) * COUT : 0;
+                        for (int tap = 0; tap < (X3 ? 18 : 9); ++tap) {         // x3: (tap, hi), (tap, lo), ... ; lo tiles are rows [COUT, 2 COUT) of the weight map
+                            const int tp = X3 ? tap >> 1 : tap, wrow = X3 ? (tap & 1) * COUT : (lo_pass ? COUT : 0);
                             mbar_wait(b_empty(bs), bph ^ 1);
                             mbar_arrive_expect_tx(b_full(bs), COUT * RB);
                             if (!CL) tma_load_2d(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tp * p.cin + ch * CC, wrow);
@@ -169,6 +177,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // constant per operand kind, lo = base + compile-time offset of the (tap, sub-tile, k) window.
         const bool leader = elect_one();
         const uint32_t idesc = F16 ? make_idesc_f16(128, COUT) : make_idesc_bf16(128, COUT);
+        const uint32_t idesc8 = make_idesc_e4m3(128, COUT);
         const uint32_t layout = RB == 128 ? 2u : RB == 64 ? 4u : 6u;
         const uint32_t a_hi = (uint32_t)((18 * RB) >> 4) | (1u << 14) | (layout << 29);     // SBO = 18 patch rows
         const uint32_t b_hi = (uint32_t)((8 * RB) >> 4) | (1u << 14) | (layout << 29);      // SBO = 8 rows
@@ -182,7 +191,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // the right 8-column sub-tile of a border tile may lie entirely outside the image (24 columns at level 3 = 1.5 tiles):
             // its UMMAs are skipped, and so is its epilogue
             const int nh = ((tile / tiles_per_tx) * 16 + 8 < p.wo) ? 2 : 1;
-            for (int ch = 0; ch < p.chunks; ++ch) {
+            for (int ch = 0; ch < n_chunk_steps; ++ch) {
+                const bool lo_pass = F8 && ch < p.chunks;
+                const bool first_main = F8 && ch == p.chunks;        // x2: the first FP16 instruction of each sub-tile rescales its accumulator
                 mbar_wait(a_full(as), aph);
                 tc_fence_after();
                 const uint32_t a_lo = (((smem_base + as * Cfg::PATCH_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
@@ -213,9 +224,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 if (h < nh)
 #pragma unroll
                                 for (int k = 0; k < CC / 16; ++k) {
+                                    if (F8) {
+                                        if (lo_pass) umma_f8_lohi(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi, idesc8,
+                                                                  (ch | tap | k) != 0 ? 1u : 0u);
+                                        else if (first_main && tap == 0 && k == 0) umma_f16_lohi_rescale(d0 + h * COUT, w_lo + ((8 * h * RB) >> 4), a_hi, b_lo, b_hi, idesc);
+                                        else umma_bf16_lohi(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi, idesc, 1u);
+                                        continue;
+                                    }
                                     umma_bf16_lohi(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi,
                                                    idesc, (ch | tap | k) != 0 ? 1u : 0u);
-                                    if (SPLIT)                                                       // lo patch . hi weights
+                                    if (X3)                                                          // lo patch . hi weights
                                         umma_bf16_lohi(d0 + h * COUT, w_lo + ((Cfg::PLANE_BYTES + 8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4),
                                                        b_hi, idesc, 1u);
                                 }
@@ -223,7 +241,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                         __syncwarp();
                         if (++bs == BST) { bs = 0; bph ^= 1; }
-                        if (SPLIT) {                                                                 // hi patch . lo weights (next ring slot)
+                        if (X3) {                                                                    // hi patch . lo weights (next ring slot)
                             mbar_wait(b_full(bs), bph);
                             tc_fence_after();
                             const uint32_t bl_lo = (((b_base + bs * Cfg::B_TILE) & 0x3FFFF) >> 4) | (1u << 16);
@@ -286,10 +304,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 for (int j = 0; j < 16; j += 4) {
                                     const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + 16 * c8 + j);
                                     const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + 16 * c8 + j);
-                                    bn_relu_split<F16>(v[16 * c8 + j], v[16 * c8 + j + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[j / 2], ol[j / 2]);
-                                    bn_relu_split<F16>(v[16 * c8 + j + 2], v[16 * c8 + j + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[j / 2 + 1],
-                                                       ol[j / 2 + 1]);
+                                    bn_relu_split<F16, F8>(v[16 * c8 + j], v[16 * c8 + j + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[j / 2], ol[j / 2]);
+                                    bn_relu_split<F16, F8>(v[16 * c8 + j + 2], v[16 * c8 + j + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[j / 2 + 1],
+                                                           ol[j / 2 + 1]);
                                 }
+                                if (F8) x2_regroup(ol);
                                 if (live) { stg256(dst + c + 16 * c8, oh); stg256(dst + p.out_lo + c + 16 * c8, ol); }
                             }
                             continue;

@@ -56,7 +56,7 @@ struct HeadTsCfg {
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-template <int NC, bool F16, bool SPLIT = false>
+template <int NC, bool F16, bool SPLIT = false, bool F8 = false>
 __global__ void __launch_bounds__(H4_THREADS, 1)
 head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadParams p) {
     using namespace tc;
@@ -171,8 +171,13 @@ head_ts_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
             mbar_wait(BAR(B0_FULL + s), ph);
             tc_fence_after();
             if (leader) {
+                if (F8) {    // x2 scheme: the lo plane of b0 and of Wsd0 are FP8 correction operands (one K = 32 step), then the FP16 term rescales
+                    umma_ts_f8_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 16 + 8, wsd_lo + (HM_WSD >> 4), HI32, make_idesc_e4m3(128, 32), 0u);
+                    umma_ts_lohi_rescale(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 16, wsd_lo, HI32, idesc_sd);
+                } else {
                 umma_ts_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 8 * PL, wsd_lo, HI32, idesc_sd, 0u);
-                if (SPLIT) {
+                }
+                if (SPLIT && !F8) {
                     umma_ts_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 16 + 8, wsd_lo, HI32, idesc_sd, 1u);                   // lo . hi
                     umma_ts_lohi(tmem_base + H4_D0 + d * 32, tmem_base + H4_B0 + s * 16, wsd_lo + (HM_WSD >> 4), HI32, idesc_sd, 1u);       // hi . lo
                 }

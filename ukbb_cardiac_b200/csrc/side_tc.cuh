@@ -76,7 +76,10 @@ __device__ __forceinline__ void plain_split(uint32_t a0, uint32_t a1, uint32_t& 
 }
 }  // namespace tc
 
-template <bool F16, bool SPLIT = false>
+// F8 (x2 scheme, tc_common.cuh): the lo planes of the INPUTS and of the same_dim weights hold FP8 correction operands.  S0 streams its K
+// chunks, so the "corrections first, then rescale" order of the convolution kernels is not available: the FP8 products go to a second
+// accumulator (D0C) and E0 adds D0C * 2^-15.  s_l (A1) and the fc0 block stay (hi, lo) FP16 pairs: A1 is produced in this kernel.
+template <bool F16, bool SPLIT = false, bool F8 = false>
 __global__ void __launch_bounds__(SD_THREADS, 1)
 side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ SideParams p) {
     using namespace tc;
@@ -99,6 +102,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
     float* s_scale = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 256);      // [4][32]
     float* s_shift = s_scale + 128;
     constexpr int D0_COL = 0, D1_COL = 64, A1_COL = 192;  // TMEM columns: 2 x 32, 2 x 64, (SPLIT) A1 2 x (16 hi + 16 lo)
+    constexpr int D0C_COL = 256, TMEM_COLS = F8 ? 512 : 256;             // (F8) correction accumulators 2 x 32
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.tile_start[4];
@@ -117,7 +121,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
         }
         fence_barrier_init();
     }
-    if (warp == 2) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    if (warp == 2) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
     if (warp == 3) {
         for (int i = lane; i < 128; i += 32) { s_scale[i] = p.scale[i >> 5][i & 31]; s_shift[i] = p.shift[i >> 5][i & 31]; }
     }
@@ -167,6 +171,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
         // ===================== MMA issuer 0: same_dim (S0) =====================
         const bool leader = elect_one();
         const uint32_t idesc = F16 ? make_idesc_f16(128, 32) : make_idesc_bf16(128, 32);
+        const uint32_t idesc8 = make_idesc_e4m3(128, 32);
         mbar_wait(BAR(WFULL), 0);
         tc_fence_after();
         int slot = 0;
@@ -189,7 +194,10 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
                 if (leader) {
                     for (int k = 0; k < ksteps; ++k) {
                         umma_bf16_lohi(d, a_lo + 2 * k, hi, w_lo + c * (4096 >> 4) + 2 * k, hi, idesc, (c | k) != 0 ? 1u : 0u);
-                        if (SPLIT) {
+                        if (F8) {
+                            umma_f8_lohi(d + (D0C_COL - D0_COL), a_lo + (SD_SLOT >> 4) + 2 * k, hi, w_lo + (SD_WSD_BYTES >> 4) + c * (4096 >> 4) + 2 * k, hi,
+                                         idesc8, (c | k) != 0 ? 1u : 0u);
+                        } else if (SPLIT) {
                             umma_bf16_lohi(d, a_lo + (SD_SLOT >> 4) + 2 * k, hi, w_lo + c * (4096 >> 4) + 2 * k, hi, idesc, 1u);              // lo . hi
                             umma_bf16_lohi(d, a_lo + 2 * k, hi, w_lo + (SD_WSD_BYTES >> 4) + c * (4096 >> 4) + 2 * k, hi, idesc, 1u);        // hi . lo
                         }
@@ -247,6 +255,13 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
             tc_fence_after();
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + D0_COL + b * 32, v);
+            if (F8) {
+                uint32_t vc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + D0C_COL + b * 32, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(vc[j]), 1.f / 32768.f, __uint_as_float(v[j])));
+            }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -350,7 +365,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 

@@ -157,6 +157,71 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- "x2" scheme (UKBB_MODE_FP16X2): the FP16 main term plus BOTH correction terms of the split product in ONE FP8 pass.
+// Every 16-channel group of the lo plane holds [e4m3(lo * 2^11) x 16 | e4m3(hi) x 16] (32 bytes, the size of 16 FP16 lo values, so
+// every layout, descriptor and store of the x3 scheme is unchanged) and the weights' lo plane [e4m3(w_hi * 2^4) x 16 | e4m3(w_lo * 2^15) x 16]:
+// one kind::f8f6f4 instruction (K = 32) per group accumulates (a_lo w_hi + a_hi w_lo) * 2^15.  All FP8 instructions of an
+// accumulator are issued first; the FIRST kind::f16 instruction then rescales it with scale-input-d = 15 (D <- A.B + D * 2^-15).
+// Measured on B200 (experiments/x2f8_probe.cu): bit-identical to this model, relative rms error of a product 9.6e-6.
+constexpr int X2_SA = 11, X2_SW_HI = 4, X2_SW_LO = 15;
+// instruction descriptor kind::f8f6f4: E4M3 x E4M3 -> F32 (a_format = b_format = 0), K-major operands
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D <- A.B + D * 2^-15 (kind::f16 with scale-input-d)
+__device__ __forceinline__ void umma_f16_lohi_rescale(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p, 15;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+        : "memory");
+}
+// same two with the A operand in tensor memory
+__device__ __forceinline__ void umma_ts_f8_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_lohi_rescale(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p, 15;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc)
+        : "memory");
+}
+
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -256,9 +321,18 @@ __device__ __forceinline__ float2 unpack16t(uint32_t u) {
 }
 // split-operand ("x3") modes: a pair of FP32 values -> 16-bit hi pieces and 16-bit lo pieces, v ~ hi + lo with hi = rn16(v) and
 // lo = rn16(v - hi) (v - hi is exact in FP32).  FP16: hi is clamped to the finite range; inputs are >= 0 (post-ReLU) or small.
-template <bool F16>
+// F8 (x2 scheme, FP16 only): `lo` receives [e4m3 pair of (a - hi) * 2^11 | e4m3 pair of hi << 16]; after the eight pairs of a 16-channel
+// group, x2_regroup() turns the eight words into the group layout [lo8 x 16 | hi8 x 16].
+template <bool F16, bool F8 = false>
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
-    if (F16) {
+    if (F8) {
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        uint16_t l8, h8;
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l8) : "f"((b - h.y) * 2048.f), "f"((a - h.x) * 2048.f));
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h8) : "f"(h.y), "f"(h.x));
+        lo = (uint32_t)l8 | ((uint32_t)h8 << 16);
+    } else if (F16) {
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
         const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - h.y), "f"(a - h.x));
@@ -266,6 +340,17 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - __uint_as_float(hi & 0xffff0000u)), "f"(a - __uint_as_float(hi << 16)));
     }
+}
+// eight words [lo8 pair | hi8 pair << 16] (channel pairs 0..7 of a 16-channel group) -> [lo8 x 16 (4 words) | hi8 x 16 (4 words)]
+__device__ __forceinline__ void x2_regroup(uint32_t (&w)[8]) {
+    uint32_t r[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r[k] = __byte_perm(w[2 * k], w[2 * k + 1], 0x5410);          // lo halves
+        r[4 + k] = __byte_perm(w[2 * k], w[2 * k + 1], 0x7632);      // hi halves
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = r[k];
 }
 __device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {
     if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&u));

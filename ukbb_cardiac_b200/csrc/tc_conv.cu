@@ -24,23 +24,27 @@ using namespace tc;
 // SPLIT (the "x3" modes): every activation and weight is the sum of two 16-bit pieces v = hi + lo (hi = rn16(v), lo = rn16(v - hi));
 // the product is accumulated as hi.hi + lo.hi + hi.lo in the same FP32 accumulator (the lo.lo term, ~2^-22 relative in FP16,
 // ~2^-16 in BF16, is dropped).  A stage then holds four operand tiles: A_hi | A_lo | B_hi | B_lo.
-template <int CC, int COUT, bool SPLIT = false>
+// F8 (x2 scheme, tc_common.cuh): the K blocks are walked TWICE -- first the lo planes (FP8 correction operands, kind::f8f6f4), then the hi
+// planes (kind::f16, the first instruction rescales the accumulator) -- so a stage holds one plane pair A | B like the plain kernel.
+template <int CC, int COUT, bool SPLIT = false, bool F8 = false>
 struct ConvTcCfg {
     static constexpr int A_BYTES = 128 * CC * 2;
     static constexpr int B_BYTES = COUT * CC * 2;
     static constexpr int B_PAD = (B_BYTES + 1023) / 1024 * 1024;
-    static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_PAD);           // all tiles 1024-aligned
+    static constexpr int PLANES = (SPLIT && !F8) ? 2 : 1;                              // operand planes per stage
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_PAD);                     // all tiles 1024-aligned
     static constexpr int MAX_STAGES = (200 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
     static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;   // power of two for COUT in {16..256}
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int CC, int COUT, bool F16, bool SPLIT = false>
+template <int CC, int COUT, bool F16, bool SPLIT = false, bool F8 = false>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcParams p) {
-    using Cfg = ConvTcCfg<CC, COUT, SPLIT>;
+    using Cfg = ConvTcCfg<CC, COUT, SPLIT, F8>;
+    constexpr bool X3 = SPLIT && !F8;
     constexpr int STAGES = Cfg::STAGES;
     griddep_launch();
     extern __shared__ uint8_t smem_raw[];
@@ -56,6 +60,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = p.cin / CC;
     const int kblocks = p.taps * chunks;
+    const int kb_total = F8 ? 2 * kblocks : kblocks;          // x2: [0, kblocks) = lo planes, [kblocks, 2 kblocks) = hi planes
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -86,16 +91,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, tn = tile / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * p.bw * p.stride - p.pad_left, y0 = ty * p.bh * p.stride - p.pad_top, n0 = tn * p.bn;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kbt = 0; kbt < kb_total; ++kbt) {
+                    const int kb = (F8 && kbt >= kblocks) ? kbt - kblocks : kbt;
+                    const bool lo_pass = F8 && kbt < kblocks;
                     const int tap = kb / chunks, ch = kb - tap * chunks;
                     const int ky = tap / p.ks, kx = tap - ky * p.ks;
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t b_dst = a_dst + (SPLIT ? 2 : 1) * Cfg::A_BYTES;
-                    mbar_arrive_expect_tx(full_bar(stage), (SPLIT ? 2 : 1) * (Cfg::A_BYTES + Cfg::B_BYTES));
-                    tma_load_4d(a_dst, &map_a, full_bar(stage), ch * CC, x0 + kx, y0 + ky, n0);
-                    tma_load_2d(b_dst, &map_b, full_bar(stage), p.kofs + tap * p.cin + ch * CC, 0);
-                    if (SPLIT) {                 // lo planes: slices [lo_n, ...) of the activation map, rows [COUT, 2 COUT) of the weight map
+                    const uint32_t b_dst = a_dst + Cfg::PLANES * Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), Cfg::PLANES * (Cfg::A_BYTES + Cfg::B_BYTES));
+                    tma_load_4d(a_dst, &map_a, full_bar(stage), ch * CC, x0 + kx, y0 + ky, (lo_pass ? p.lo_n : 0) + n0);
+                    tma_load_2d(b_dst, &map_b, full_bar(stage), p.kofs + tap * p.cin + ch * CC, lo_pass ? COUT : 0);
+                    if (X3) {                    // lo planes: slices [lo_n, ...) of the activation map, rows [COUT, 2 COUT) of the weight map
                         tma_load_4d(a_dst + Cfg::A_BYTES, &map_a, full_bar(stage), ch * CC, x0 + kx, y0 + ky, p.lo_n + n0);
                         tma_load_2d(b_dst + Cfg::B_PAD, &map_b, full_bar(stage), p.kofs + tap * p.cin + ch * CC, COUT);
                     }
@@ -107,6 +114,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
         const bool leader = elect_one();
         const uint32_t idesc = F16 ? make_idesc_f16(128, COUT) : make_idesc_bf16(128, COUT);
+        const uint32_t idesc8 = make_idesc_e4m3(128, COUT);
         constexpr uint32_t RB = CC * 2;
         constexpr uint32_t HI = (uint32_t)((8 * RB) >> 4) | (1u << 14) | ((RB == 128 ? 2u : RB == 64 ? 4u : 6u) << 29);
         int stage = 0;
@@ -117,22 +125,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(tempty_bar(acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d = tmem_base + acc * COUT;
-            for (int kb = 0; kb < kblocks; ++kb) {
+            for (int kb = 0; kb < kb_total; ++kb) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 const uint32_t a_lo = (((smem_base + stage * Cfg::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
-                const uint32_t b_lo = a_lo + (((SPLIT ? 2 : 1) * Cfg::A_BYTES) >> 4);
+                const uint32_t b_lo = a_lo + ((Cfg::PLANES * Cfg::A_BYTES) >> 4);
                 if (leader) {
 #pragma unroll
                     for (int k = 0; k < CC / 16; ++k) {
+                        if (F8) {
+                            if (kb < kblocks) umma_f8_lohi(d, a_lo + 2 * k, HI, b_lo + 2 * k, HI, idesc8, (kb | k) != 0 ? 1u : 0u);
+                            else if (kb == kblocks && k == 0) umma_f16_lohi_rescale(d, a_lo, HI, b_lo, HI, idesc);
+                            else umma_bf16_lohi(d, a_lo + 2 * k, HI, b_lo + 2 * k, HI, idesc, 1u);
+                            continue;
+                        }
                         umma_bf16_lohi(d, a_lo + 2 * k, HI, b_lo + 2 * k, HI, idesc, (kb | k) != 0 ? 1u : 0u);
-                        if (SPLIT) {
+                        if (X3) {
                             umma_bf16_lohi(d, a_lo + (Cfg::A_BYTES >> 4) + 2 * k, HI, b_lo + 2 * k, HI, idesc, 1u);                  // lo . hi
                             umma_bf16_lohi(d, a_lo + 2 * k, HI, b_lo + (Cfg::B_PAD >> 4) + 2 * k, HI, idesc, 1u);                    // hi . lo
                         }
                     }
                     umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
-                    if (kb == kblocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+                    if (kb == kb_total - 1) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -169,13 +183,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
                     else if (F16) { a0 = fmaxf(a0, -65504.f); a1 = fmaxf(a1, -65504.f); a2 = fmaxf(a2, -65504.f); a3 = fmaxf(a3, -65504.f); }
                     if (SPLIT) {
-                        split_pack<F16>(a0, a1, o[2 * j4], ol[2 * j4]);
-                        split_pack<F16>(a2, a3, o[2 * j4 + 1], ol[2 * j4 + 1]);
+                        split_pack<F16, F8>(a0, a1, o[2 * j4], ol[2 * j4]);
+                        split_pack<F16, F8>(a2, a3, o[2 * j4 + 1], ol[2 * j4 + 1]);
                     } else {
                         o[2 * j4] = pack16t<F16>(a0, a1);
                         o[2 * j4 + 1] = pack16t<F16>(a2, a3);
                     }
                 }
+                if (F8) x2_regroup(ol);
                 if (live) {
                     uint4* d4 = reinterpret_cast<uint4*>(dst + c);
                     d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -204,16 +219,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // Launchers of the three convolution kernel families
 // ------------------------------------------------------------------------------------------
-template <int CC, int COUT, bool F16, bool SPLIT>
+template <int CC, int COUT, bool F16, bool SPLIT, bool F8 = false>
 static int launch_tc2(const TcLayerPlan& P, int sms, cudaStream_t st) {
-    using Cfg = ConvTcCfg<CC, COUT, SPLIT>;
+    using Cfg = ConvTcCfg<CC, COUT, SPLIT, F8>;
     static bool attr_set = false;
     if (!attr_set) {
-        UKBB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CC, COUT, F16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        UKBB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CC, COUT, F16, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = P.p.n_tiles < sms ? P.p.n_tiles : sms;
-    UKBB_CUDA(launch_pdl(conv_tc_kernel<CC, COUT, F16, SPLIT>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.p));
+    UKBB_CUDA(launch_pdl(conv_tc_kernel<CC, COUT, F16, SPLIT, F8>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.p));
     return UKBB_OK;
 }
 template <int CC, int COUT>
@@ -226,17 +241,17 @@ static int launch_tc_x3(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st
 }
 
 // levels 3 / 4: streamed weights, clusters of two CTAs share every weight tile through TMA multicast (conv_halo.cuh)
-template <int CC, int COUT, bool F16, bool SPLIT>
+template <int CC, int COUT, bool F16, bool SPLIT, bool F8 = false>
 static int launch_halo2(const TcLayerPlan& P, int sms, cudaStream_t st) {
-    using Cfg = ConvHaloCfg<CC, COUT, false, 0, SPLIT>;
+    using Cfg = ConvHaloCfg<CC, COUT, false, 0, SPLIT, F8>;
     static bool attr_set = false;
     if (!attr_set) {
-        UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int pairs = (P.hp.n_tiles + 1) / 2;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
-    UKBB_CUDA(launch_pdl<2>(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.hp));
+    UKBB_CUDA(launch_pdl<2>(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT, F8>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.hp));
     return UKBB_OK;
 }
 template <int CC, int COUT, bool SPLIT>
@@ -244,16 +259,16 @@ static int launch_halo(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st)
     return fp16 ? launch_halo2<CC, COUT, true, SPLIT>(P, sms, st) : launch_halo2<CC, COUT, false, SPLIT>(P, sms, st);
 }
 
-template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT>
+template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT, bool F8 = false>
 static int launch_group2(const TcLayerPlan& P, int sms, cudaStream_t st) {
-    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT>;
+    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT, F8>;
     static bool attr_set = false;
     if (!attr_set) {
-        UKBB_CUDA(cudaFuncSetAttribute(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        UKBB_CUDA(cudaFuncSetAttribute(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = P.gp.n_tiles < sms ? P.gp.n_tiles : sms;
-    UKBB_CUDA(launch_pdl(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.map_out, P.gp));
+    UKBB_CUDA(launch_pdl(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT, F8>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.map_out, P.gp));
     return UKBB_OK;
 }
 template <int CC, int COUT, int STRIDE, bool SPLIT>
@@ -262,6 +277,21 @@ static int launch_group(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st
 }
 
 int launch_plan(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st) {
+    if (P.f8) {                     // x2 scheme (FP16 pieces + FP8 corrections): same plans and tile shapes as the x3 instances
+        if (P.kind == 2) {
+#define GCASE(CIN, COUTV, S) if (P.p.cin == CIN && P.cout == COUTV && P.p.stride == S) return launch_group2<CIN, COUTV, S, true, true, true>(P, sms, st)
+            GCASE(16, 16, 1); GCASE(32, 32, 1); GCASE(64, 64, 1); GCASE(16, 32, 2); GCASE(32, 64, 2);
+#undef GCASE
+        } else if (P.kind == 1) {
+            if (P.cc == 32 && P.cout == 128) return launch_halo2<32, 128, true, true, true>(P, sms, st);
+            if (P.cc == 32 && P.cout == 256) return launch_halo2<32, 256, true, true, true>(P, sms, st);
+        } else {
+            if (P.cc == 64 && P.cout == 128) return launch_tc2<64, 128, true, true, true>(P, sms, st);
+            if (P.cc == 64 && P.cout == 256) return launch_tc2<64, 256, true, true, true>(P, sms, st);
+        }
+        set_error("x2 scheme: no kernel instance for kind %d, chunk %d, %d -> %d stride %d", P.kind, P.cc, P.p.cin, P.cout, P.p.stride);
+        return UKBB_E_UNSUPPORTED;
+    }
     if (P.kind == 2) {
 #define GCASE(CIN, COUTV, S)                                                                                         \
         if (P.p.cin == CIN && P.cout == COUTV && P.p.stride == S)                                                    \

@@ -7,6 +7,7 @@
 // is stored as two planes of the plain layout, the lo plane right after the hi plane; tensor maps span both planes (the lo
 // plane is reached through a slice / row offset), so each kernel needs one map per tensor.
 #include "tc_plan.cuh"
+#include <cuda_fp8.h>
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -23,14 +24,31 @@ static uint16_t enc16(float v, int fp16, float* back) {
     return u;
 }
 
-// float values -> device array of 16-bit values: [n] (plain) or [2][n] = hi plane | lo plane (split)
+static uint8_t enc_e4m3(float v) {
+    const __nv_fp8_e4m3 q(v);                 // round to nearest even, saturating
+    uint8_t u;
+    memcpy(&u, &q, 1);
+    return u;
+}
+
+// float values -> device array of 16-bit values: [n] (plain) or [2][n] = hi plane | lo plane (split = 1).
+// split = 2 (x2 scheme, weights side): the lo plane is the FP8 correction operand -- per group of 16 consecutive K elements (32 bytes,
+// the bytes an FP16 K = 16 step reads) [e4m3(w_hi * 2^4) x 16 | e4m3(w_lo * 2^15) x 16], the partner of the activations'
+// [e4m3(a_lo * 2^11) x 16 | e4m3(a_hi) x 16] (tc_common.cuh).  Every weight array here has K (the innermost extent) a multiple of 16.
 static int upload16(const std::vector<float>& v, int fp16, int split, __nv_bfloat16** dev) {
     const size_t n = v.size();
     std::vector<uint16_t> h((split ? 2 : 1) * n);
+    if (split == 2 && n % 16 != 0) { set_error("upload16: x2 weights need K groups of 16"); return UKBB_E_INVALID; }
+    uint8_t* lo8 = reinterpret_cast<uint8_t*>(h.data() + (split ? n : 0));
     for (size_t i = 0; i < n; ++i) {
         float hf, lf;
         h[i] = enc16(v[i], fp16, &hf);
-        if (split) h[n + i] = enc16(v[i] - hf, fp16, &lf);
+        if (split == 1) h[n + i] = enc16(v[i] - hf, fp16, &lf);
+        if (split == 2) {
+            const size_t g = i / 16, e = i % 16;
+            lo8[g * 32 + e] = enc_e4m3(ldexpf(hf, tc::X2_SW_HI));
+            lo8[g * 32 + 16 + e] = enc_e4m3(ldexpf(v[i] - hf, tc::X2_SW_LO));
+        }
     }
     UKBB_CUDA(cudaMalloc(dev, h.size() * 2));
     UKBB_CUDA(cudaMemcpy(*dev, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
@@ -60,7 +78,7 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     const int ho = (hi + s - 1) / s, wo = (wi + s - 1) / s;
     int pt = (ho - 1) * s + ks - hi; if (pt < 0) pt = 0; pt /= 2;
     int pl = (wo - 1) * s + ks - wi; if (pl < 0) pl = 0; pl /= 2;
-    P.split = split; P.cout = L.cout;
+    P.split = split; P.f8 = S->f8; P.cout = L.cout;
     P.kind = (ks == 3 && L.cin <= 64 && S->wg[li] && wi % (64 / L.cin) == 0) ? 2 : (ks == 3 && s == 1 && L.cin >= 128) ? 1 : 0;
     const int cc = (P.kind == 1 && split) ? 32 : chunk_for(L.cin);
     P.cc = cc;
@@ -152,8 +170,11 @@ int tc_prepare(Engine* h, const ukbb_fcn_weights* w) {
     if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return UKBB_E_CUDA; }
     S->encode = (EncodeTiledFn)fn;
     S->fp16 = (h->mode == UKBB_MODE_FP16 || h->mode == UKBB_MODE_FP16X3) ? 1 : 0;
-    S->split = (h->mode == UKBB_MODE_BF16X3 || h->mode == UKBB_MODE_FP16X3) ? 1 : 0;
+    S->fp16 = S->fp16 || h->mode == UKBB_MODE_FP16X2;
+    S->f8 = h->mode == UKBB_MODE_FP16X2 ? 1 : 0;
+    S->split = (h->mode == UKBB_MODE_BF16X3 || h->mode == UKBB_MODE_FP16X3 || S->f8) ? 1 : 0;
     const int fp16 = S->fp16, split = S->split;
+    const int wsplit = S->f8 ? 2 : split;      // weights of the layers that read tensors from HBM: FP8 correction plane in the x2 scheme
     int rc;
     {   // class-score layer: FP32 weights [k][8] and bias, passed by value (constant bank)
         const ukbb_conv_weights& c = w->conv[UKBB_N_CONV - 1];
@@ -203,7 +224,7 @@ int tc_prepare(Engine* h, const ukbb_fcn_weights* w) {
             S->h_shift[li][co] = (float)((double)c.beta[co] - (double)c.moving_mean[co] * sc);
             for (int ci = 0; ci < c.cin; ++ci) wb[(size_t)co * c.cin + ci] = (float)((double)c.kernel[(size_t)ci * c.cout + co] * sc);
         }
-        rc = upload16(wb, fp16, split, &S->wf[li]);
+        rc = upload16(wb, fp16, li == 13 ? wsplit : split, &S->wf[li]);      // fc0 / fc1 multiply operands made in the kernel: (hi, lo) FP16
         if (rc) return rc;
     }
     for (int l = 1; l <= 4; ++l) {         // interpolation matrices of the tensor-core upsample (head_common.cuh); exact in 16 bits
@@ -233,7 +254,7 @@ int tc_prepare(Engine* h, const ukbb_fcn_weights* w) {
                 for (int ci = 0; ci < c.cin; ++ci)
                     for (int co = 0; co < c.cout; ++co)      // device tap (dy,dx) <- TF kernel[kh=dx][kw=dy]
                         wb[(size_t)co * ktot + (dy * c.ksize + dx) * c.cin + ci] = c.kernel[((size_t)(dx * c.ksize + dy) * c.cin + ci) * c.cout + co];
-        rc = upload16(wb, fp16, split, &S->w[i]);
+        rc = upload16(wb, fp16, wsplit, &S->w[i]);
         if (rc) return rc;
         // pixel-group layers (conv_group.cuh): N = gout * cout = 64.  Tile (ky, j) row (s, co) holds tap (ky, kx) with
         // kx = j - s (stride 1) or j - 2 s (stride 2), zero where that tap does not exist.
@@ -251,7 +272,7 @@ int tc_prepare(Engine* h, const ukbb_fcn_weights* w) {
                                     if (kx >= 0 && kx <= 2)
                                         we[((size_t)(ky * jn + j) * 64 + sp * c.cout + co) * c.cin + ci] = wb[(size_t)co * ktot + (ky * 3 + kx) * c.cin + ci];
                                 }
-                rc = upload16(we, fp16, split, &S->wg[i]);
+                rc = upload16(we, fp16, wsplit, &S->wg[i]);
                 if (rc) return rc;
             }
         }
@@ -368,11 +389,18 @@ int debug_conv_tc(Engine* h, int li, const void* in, int n, int hi, int wi, int 
     return rc;
 }
 
-__global__ void widen16_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, float* __restrict__ out, long long n, int fp16) {
+// lo plane formats: 0 = none, 1 = 16-bit values, 2 = x2 scheme (per 16 elements [e4m3(lo * 2^11) x 16 | e4m3(hi) x 16])
+__global__ void widen16_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, float* __restrict__ out, long long n, int fp16, int lo_fmt) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     auto cv = [&](uint16_t u) { return fp16 ? __half2float(__ushort_as_half(u)) : __uint_as_float((uint32_t)u << 16); };
-    out[i] = cv(hi[i]) + (lo ? cv(lo[i]) : 0.f);
+    float l = 0.f;
+    if (lo_fmt == 1) l = cv(lo[i]);
+    if (lo_fmt == 2) {
+        const __nv_fp8_storage_t b = reinterpret_cast<const uint8_t*>(lo)[(i / 16) * 32 + (i % 16)];
+        l = __half2float(__half(__nv_cvt_fp8_to_halfraw(b, __NV_E4M3))) * (1.f / (float)(1 << tc::X2_SA));
+    }
+    out[i] = cv(hi[i]) + l;
 }
 
 // Test hook: copy an intermediate tensor of the most recent forward out as FP32 (hi + lo in the split modes).
@@ -385,7 +413,8 @@ int debug_read_tc(Engine* h, int which, int level, float* out, long long n_elems
     UKBB_REQUIRE(src, "debug_read: tensor %d of level %d is not materialised", which, level);
     const size_t plane = (size_t)S->plan_nb * (S->plan_h >> level) * (S->plan_w >> level) * (which == 2 ? 64 : kNFilterTc[level]);
     UKBB_REQUIRE(n_elems > 0 && (size_t)n_elems <= plane, "debug_read: %lld elements requested, the tensor has %zu", n_elems, plane);
-    widen16_kernel<<<(unsigned)((n_elems + 255) / 256), 256, 0, st>>>(src, S->split ? src + plane : nullptr, out, n_elems, S->fp16);
+    const int lo_fmt = !S->split ? 0 : (S->f8 && which != 2) ? 2 : 1;          // t_l stays a (hi, lo) FP16 pair in the x2 scheme
+    widen16_kernel<<<(unsigned)((n_elems + 255) / 256), 256, 0, st>>>(src, src + plane, out, n_elems, S->fp16, lo_fmt);
     UKBB_CUDA(cudaGetLastError());
     return UKBB_OK;
 }
@@ -448,7 +477,7 @@ int forward_tc(Engine* h, const float* image, int n, int x2, int y2, int x_pre, 
                 sp.t[l - 1] = (uint32_t*)S->t[l]; sp.t_lo[l - 1] = cap_rows * 32;
             }
             sp.tile_start[4] = acc_tiles;
-            rc = S->split ? launch_side_x3(S, sp, h->sms, st) : launch_side_16(S, sp, h->sms, st);
+            rc = S->f8 ? launch_side_x2(S, sp, h->sms, st) : S->split ? launch_side_x3(S, sp, h->sms, st) : launch_side_16(S, sp, h->sms, st);
             if (rc) return rc;
             h->launches++;
         }
@@ -483,7 +512,8 @@ int forward_tc(Engine* h, const float* image, int n, int x2, int y2, int x_pre, 
                 UKBB_CUDA(cudaEventCreate(&kt0)); UKBB_CUDA(cudaEventCreate(&kt1));
                 UKBB_CUDA(cudaEventRecord(kt0, st));
             }
-            rc = S->split ? launch_head_x3(S, hp, h->n_class, h->sms, st) : launch_head_16(S, hp, h->n_class, h->sms, st);
+            rc = S->f8 ? launch_head_x2(S, hp, h->n_class, h->sms, st)
+                 : S->split ? launch_head_x3(S, hp, h->n_class, h->sms, st) : launch_head_16(S, hp, h->n_class, h->sms, st);
             if (h->ktimer && !rc) { UKBB_CUDA(cudaEventRecord(kt1, st)); h->ktimer_ev.emplace_back(kt0, kt1); }
             if (rc) return rc;
             h->launches++;

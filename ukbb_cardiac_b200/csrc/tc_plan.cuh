@@ -43,13 +43,15 @@ struct TcLayerPlan {
     int kind = 0;                   // 0 = per-tap implicit GEMM (conv_tc_kernel), 1 = halo reuse, streamed weights (conv_halo_kernel),
                                     // 2 = pixel-group rows (conv_group_kernel)
     int split = 0;
+    int f8 = 0;                     // split scheme with FP8 correction operands in the lo planes (UKBB_MODE_FP16X2)
     bool valid = false;
 };
 
 struct TcState {
     EncodeTiledFn encode = nullptr;
     int fp16 = 0;                            // 16-bit operand format: 0 = BF16, 1 = FP16
-    int split = 0;                           // x3 modes: every operand is a (hi, lo) pair, second plane right after the first
+    int split = 0;                           // x3 / x2 modes: every operand is a (hi, lo) pair, second plane right after the first
+    int f8 = 0;                              // x2 mode: the lo plane holds FP8 correction operands (tc_common.cuh: split_pack<.., true>)
     __nv_bfloat16* w[UKBB_N_CONV] = {};      // [planes][cout][taps*cin], K-major
     __nv_bfloat16* wg[UKBB_N_CONV] = {};     // pixel-group layers: expanded [planes][3 * J tiles][64 rows][cin] (conv_group.cuh)
     __nv_bfloat16* wf[UKBB_N_CONV] = {};     // same_dim0 / fc0 / fc1 with the BN scale folded in before rounding: [planes][cout][cin]
@@ -97,5 +99,8 @@ int launch_side_16(const TcState* S, const SideParams& sp, int sms, cudaStream_t
 int launch_head_16(const TcState* S, const HeadParams& hp, int n_class, int sms, cudaStream_t st);
 int launch_side_x3(const TcState* S, const SideParams& sp, int sms, cudaStream_t st);
 int launch_head_x3(const TcState* S, const HeadParams& hp, int n_class, int sms, cudaStream_t st);
+// tc_head_x2.cu (FP16 pieces + FP8 correction operands)
+int launch_side_x2(const TcState* S, const SideParams& sp, int sms, cudaStream_t st);
+int launch_head_x2(const TcState* S, const HeadParams& hp, int n_class, int sms, cudaStream_t st);
 
 }  // namespace ukbb
