@@ -41,6 +41,7 @@ struct ConvFirstParams {
     float shift0[16];               // conv0_0 folded BN shift (the scale is folded into its weights)
     uint32_t* out;                  // split modes: b0 hi plane [n][h][w4 groups][64 elements] as 32-bit words
     long long out_lo;               //              offset of the lo plane in 32-bit words
+    int lo_n;                       //              slice index of the lo plane in the output tensor map
 };
 
 namespace tc {
@@ -66,7 +67,7 @@ struct ConvFirstTcCfg {
     static constexpr int B_SET = NB_TILES * B_TILE;
     static constexpr int B_BYTES = (SPLIT ? 2 : 1) * B_SET;     // hi tiles | lo tiles
     static constexpr int B0_BYTES = 64 * 128;                   // conv0_0 weights [64 rows][64 K] 16-bit, 128 B swizzle
-    static constexpr int OUT_BYTES = SPLIT ? 0 : 128 * 128;
+    static constexpr int OUT_BYTES = 128 * 128;                // staging tiles of the TMA store: two tiles (plain) / hi + lo tile of one (SPLIT)
     static constexpr int IMG_W = 48, IMG_H = 20;                // FP32 box: columns x0 - 8 .. x0 + 39, rows y0 - 2 .. y0 + 17 (TMA needs the
                                                                 // box origin 16-byte aligned in the inner dimension: experiments/tma_probe_img.cu)
     static constexpr int IMG_TX = IMG_W * IMG_H * 4;
@@ -253,6 +254,9 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         TileWalk w;
         w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+        float sh0[16];                                                           // conv0_0 shifts: registers, not one LDC per use
+#pragma unroll
+        for (int c = 0; c < 16; ++c) sh0[c] = p.shift0[c];
         auto build = [&](int j) {                                                // A0 of tile j -> TMEM stage j & 1
             const int s = j & 1, is = j % IST;
             mbar_wait(BAR(IMG_FULL + is), (uint32_t)(j / IST) & 1u);
@@ -325,11 +329,12 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                 for (int qt = 0; qt < 4; ++qt) {
                     uint32_t oh[8], ol[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        add_relu_split<F16, F8>(d[16 * qt + 2 * c], d[16 * qt + 2 * c + 1], p.shift0[2 * c], p.shift0[2 * c + 1], oh[c], ol[c]);
-                        if (!inside) { oh[c] = 0u; ol[c] = 0u; }
+                    for (int c = 0; c < 4; ++c)
+                        add_relu_split4<F16, F8>(d + 16 * qt + 4 * c, sh0 + 4 * c, oh, ol, c);
+                    if (!inside) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) { oh[c] = 0u; ol[c] = 0u; }
                     }
-                    if (F8) x2_regroup(ol);
                     if (active) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
@@ -385,14 +390,18 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
         w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
         int acc = 0;
         uint32_t acc_ph = 0;
+        float4 scv[4], shv[4];                               // conv0_1 folded BN of the 16 channels (column c -> channel c & 15)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { scv[c] = *reinterpret_cast<const float4*>(s_scale + 4 * c); shv[c] = *reinterpret_cast<const float4*>(s_shift + 4 * c); }
         for (int i = 0; i < my_tiles; ++i) {
             mbar_wait(tfull(acc), acc_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::COL_ACC + acc * Cfg::ACC_COLS;
             if (SPLIT) {
-                const int y = w.ty * 16 + (r >> 3), gx = w.tx * 8 + (r & 7);
-                const bool live = y < p.h && gx < p.w4;
-                uint32_t* dst = p.out + (((size_t)w.n * p.h + y) * p.w4 + gx) * 32;
+                // The tile leaves through a swizzled staging tile per plane and two TMA stores: a thread owns one 128-byte row, and 32-byte
+                // stores from 32 threads to 32 different lines cost 32 LSU wavefronts each (the LSU data pipe was 82 % busy, the bound of
+                // this kernel: profiles/r2_ncu_summary.txt); STS.128 are conflict-free (4 wavefronts) and the async proxy does the rest.
+                const uint32_t row = out_base + r * 128;
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     uint32_t v[16], v2[16], oh[8], ol[8];
@@ -409,14 +418,26 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
                         for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
                     }
 #pragma unroll
-                    for (int c = 0; c < 16; c += 4) {
-                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
-                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
-                        bn_relu_split<F16, F8>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
-                        bn_relu_split<F16, F8>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1], ol[c / 2 + 1]);
+                    for (int c = 0; c < 16; c += 4) bn_relu_split4<F16, F8>(v + c, scv[c / 4], shv[c / 4], oh, ol, c / 4);
+                    if (c8 == 0) {                                   // the stores of the previous tile have read the staging tiles
+                        if (issuer) bulk_wait_read<0>();
+                        named_bar_sync(1, 128);
                     }
-                    if (F8) x2_regroup(ol);
-                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t dst = row + ((uint32_t)((2 * c8 + k) ^ (r & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(oh[4 * k]), "r"(oh[4 * k + 1]), "r"(oh[4 * k + 2]),
+                                     "r"(oh[4 * k + 3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + Cfg::OUT_BYTES), "r"(ol[4 * k]), "r"(ol[4 * k + 1]),
+                                     "r"(ol[4 * k + 2]), "r"(ol[4 * k + 3]) : "memory");
+                    }
+                }
+                fence_proxy_async();
+                named_bar_sync(1, 128);
+                if (issuer) {
+                    tma_store_4d(&map_out, out_base, 0, w.tx * 8, w.ty * 16, w.n);
+                    tma_store_4d(&map_out, out_base + Cfg::OUT_BYTES, 0, w.tx * 8, w.ty * 16, w.n + p.lo_n);
+                    bulk_commit();
                 }
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
                 w.next();
@@ -455,7 +476,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_c
             }
             w.next();
         }
-        if (issuer && !SPLIT) bulk_wait<0>();
+        if (issuer) bulk_wait<0>();
     }
     tc_fence_before();
     __syncthreads();

@@ -68,7 +68,11 @@ struct ConvGroupCfg {
     static constexpr int NB_TILES = 3 * J;
     static constexpr int B_SET = NB_TILES * B_TILE;
     static constexpr int B_BYTES = (SPLIT ? 2 : 1) * B_SET;    // hi tiles | lo tiles
-    static constexpr int OUT_BYTES = SPLIT ? 0 : 128 * 128;    // staging tile [128 rows][128 B]
+    // SPLIT: the output leaves through one (hi, lo) pair of staging tiles and two TMA stores where two patch stages leave room for them
+    // (32 -> 32): a thread owns a 128-byte row and its 32-byte global stores cost one LSU wavefront per lane (32 lines per instruction);
+    // the other split instances keep the direct 256-bit stores.
+    static constexpr bool STAGED = SPLIT && TROWS == 16 && 2 * A_STAGE_BYTES + B_BYTES + 2 * 128 * 128 + 1024 + 256 + 2 * N * 4 <= 227 * 1024;
+    static constexpr int OUT_BYTES = (SPLIT && !STAGED) ? 0 : 128 * 128;    // staging tile [128 rows][128 B]
     static constexpr int A_MAX = ((SPLIT ? 224 : 200) * 1024 - B_BYTES - 2 * OUT_BYTES) / A_STAGE_BYTES;
     static constexpr int A_STAGES = A_MAX > 4 ? 4 : A_MAX;
     static constexpr int ACC_STAGES = 2;
@@ -119,6 +123,23 @@ __device__ __forceinline__ void bn_relu_split(uint32_t a0, uint32_t a1, float2 s
     float x0, x1;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
     split_pack<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
+}
+// four channels of a 16-channel group (quad q): BN + ReLU, then split_pack4 (tc_common.cuh)
+template <bool F16, bool F8>
+__device__ __forceinline__ void bn_relu_split4(const uint32_t* v, float4 sc, float4 sh, uint32_t* oh, uint32_t* ol, int q) {
+    uint64_t a, b, c, d0, d1;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(v[0]), "r"(v[1]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(sc.x), "f"(sc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(sh.x), "f"(sh.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d0) : "l"(a), "l"(b), "l"(c));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(v[2]), "r"(v[3]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(sc.z), "f"(sc.w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(sh.z), "f"(sh.w));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d1) : "l"(a), "l"(b), "l"(c));
+    float x0, x1, x2, x3;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x2), "=f"(x3) : "l"(d1));
+    split_pack4<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), fmaxf(x2, 0.f), fmaxf(x3, 0.f), oh, ol, q);
 }
 // one 256-bit global store (STG.256): a full 32-byte sector per thread
 __device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
@@ -288,16 +309,23 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
         int acc = 0;
         uint32_t acc_ph = 0;
+        // folded BN of the COUT channels in registers (SPLIT): two broadcast LDS.128 per four outputs were a tenth of the epilogue
+        float4 scv[SPLIT ? COUT / 4 : 1], shv[SPLIT ? COUT / 4 : 1];
+        if (SPLIT) {
+#pragma unroll
+            for (int c = 0; c < COUT / 4; ++c) { scv[c] = *reinterpret_cast<const float4*>(s_scale + 4 * c); shv[c] = *reinterpret_cast<const float4*>(s_shift + 4 * c); }
+        }
         for (int i = 0; i < my_tiles; ++i) {
             mbar_wait(tfull(acc), acc_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
             if (SPLIT) {
-                // acc = columns [0, 64) + columns [64, 128); hi / lo pieces, 128 contiguous bytes each per thread (this row's group),
-                // four 256-bit stores per plane
+                // acc = columns [0, 64) + columns [64, 128) (x3); hi / lo pieces, 128 contiguous bytes each per thread (this row's group):
+                // four 256-bit stores per plane, or (STAGED) swizzled staging tiles and two TMA stores
                 const int row = r >> 3, y = w.ty * TROWS + row, gx = w.tx * 8 + (r & 7);
                 const bool live = row < TROWS && y < p.ho && gx < p.wog;
                 uint32_t* dst = p.out + (((size_t)w.n * p.ho + y) * p.wog + gx) * 32;
+                const uint32_t srow = out_base + r * 128;
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     uint32_t v[16], v2[16], oh[8], ol[8];
@@ -314,14 +342,33 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
                     }
 #pragma unroll
-                    for (int c = 0; c < 16; c += 4) {
-                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 16 * c8 + c);
-                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 16 * c8 + c);
-                        bn_relu_split<F16, F8>(v[c], v[c + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[c / 2], ol[c / 2]);
-                        bn_relu_split<F16, F8>(v[c + 2], v[c + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[c / 2 + 1], ol[c / 2 + 1]);
+                    for (int c = 0; c < 16; c += 4) bn_relu_split4<F16, F8>(v + c, scv[((16 * c8 + c) % COUT) / 4], shv[((16 * c8 + c) % COUT) / 4], oh, ol, c / 4);
+                    if (Cfg::STAGED) {
+                        if (c8 == 0) {                               // the stores of the previous tile have read the staging tiles
+                            if (issuer) bulk_wait_read<0>();
+                            named_bar_sync(1, 128);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint32_t d = srow + ((uint32_t)((2 * c8 + k) ^ (r & 7)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(oh[4 * k]), "r"(oh[4 * k + 1]), "r"(oh[4 * k + 2]),
+                                         "r"(oh[4 * k + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + Cfg::OUT_BYTES), "r"(ol[4 * k]), "r"(ol[4 * k + 1]),
+                                         "r"(ol[4 * k + 2]), "r"(ol[4 * k + 3]) : "memory");
+                        }
+                    } else if (live) {
+                        stg256(dst + 8 * c8, oh);
+                        stg256(dst + p.out_lo + 8 * c8, ol);
                     }
-                    if (F8) x2_regroup(ol);
-                    if (live) { stg256(dst + 8 * c8, oh); stg256(dst + p.out_lo + 8 * c8, ol); }
+                }
+                if (Cfg::STAGED) {
+                    fence_proxy_async();
+                    named_bar_sync(1, 128);
+                    if (issuer) {
+                        tma_store_4d(&map_out, out_base, 0, w.tx * 8, w.ty * TROWS, w.n);
+                        tma_store_4d(&map_out, out_base + Cfg::OUT_BYTES, 0, w.tx * 8, w.ty * TROWS, w.n + p.lo_n);
+                        bulk_commit();
+                    }
                 }
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
                 w.next();

@@ -304,11 +304,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 for (int j = 0; j < 16; j += 4) {
                                     const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + 16 * c8 + j);
                                     const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + 16 * c8 + j);
-                                    bn_relu_split<F16, F8>(v[16 * c8 + j], v[16 * c8 + j + 1], make_float2(sc.x, sc.y), make_float2(sh.x, sh.y), oh[j / 2], ol[j / 2]);
-                                    bn_relu_split<F16, F8>(v[16 * c8 + j + 2], v[16 * c8 + j + 3], make_float2(sc.z, sc.w), make_float2(sh.z, sh.w), oh[j / 2 + 1],
-                                                           ol[j / 2 + 1]);
+                                    bn_relu_split4<F16, F8>(v + 16 * c8 + j, sc, sh, oh, ol, j / 4);
                                 }
-                                if (F8) x2_regroup(ol);
                                 if (live) { stg256(dst + c + 16 * c8, oh); stg256(dst + p.out_lo + c + 16 * c8, ol); }
                             }
                             continue;

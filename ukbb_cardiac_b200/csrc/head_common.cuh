@@ -82,6 +82,21 @@ __device__ __forceinline__ void add_relu_split(uint32_t a0, uint32_t a1, float s
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
     split_pack<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
 }
+// four channels (quad q of a 16-channel group): + shift, ReLU, split_pack4 (tc_common.cuh)
+template <bool F16, bool F8>
+__device__ __forceinline__ void add_relu_split4(const uint32_t* a, const float* s, uint32_t* oh, uint32_t* ol, int q) {
+    uint64_t x, sh, d0, d1;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(a[0]), "r"(a[1]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sh) : "f"(s[0]), "f"(s[1]));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d0) : "l"(x), "l"(sh));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(a[2]), "r"(a[3]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sh) : "f"(s[2]), "f"(s[3]));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d1) : "l"(x), "l"(sh));
+    float x0, x1, x2, x3;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x2), "=f"(x3) : "l"(d1));
+    split_pack4<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), fmaxf(x2, 0.f), fmaxf(x3, 0.f), oh, ol, q);
+}
 }  // namespace tc
 
 }  // namespace ukbb

@@ -246,11 +246,21 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
         // ===================== E0: D0 -> BN + ReLU -> A1 =====================
         const int q = warp - 4;
         const int r = q * 32 + lane;
+        float4 scv[8], shv[8];                               // (SPLIT) folded BN of the level's 32 channels in registers, reloaded when the level changes
+        int cur_l = 0;
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = blockIdx.x + i * gridDim.x;
             const int l = level_of(tile);
             const int b = i & 1;
             const uint32_t ph = ((uint32_t)i >> 1) & 1u;
+            if (SPLIT && l != cur_l) {
+                cur_l = l;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    scv[j] = *reinterpret_cast<const float4*>(s_scale + (l - 1) * 32 + 4 * j);
+                    shv[j] = *reinterpret_cast<const float4*>(s_shift + (l - 1) * 32 + 4 * j);
+                }
+            }
             mbar_wait(BAR(D0_FULL + b), ph);
             tc_fence_after();
             uint32_t v[32];
@@ -275,12 +285,7 @@ side_tc_kernel(const __grid_constant__ SideMaps maps, const __grid_constant__ Si
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t oh[8], ol[8];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 sc0 = *reinterpret_cast<const float4*>(sc + 16 * hf + j), sh0 = *reinterpret_cast<const float4*>(sh + 16 * hf + j);
-                        bn_relu_split<F16>(v[16 * hf + j], v[16 * hf + j + 1], make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y), oh[j / 2], ol[j / 2]);
-                        bn_relu_split<F16>(v[16 * hf + j + 2], v[16 * hf + j + 3], make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w), oh[j / 2 + 1],
-                                           ol[j / 2 + 1]);
-                    }
+                    for (int j = 0; j < 16; j += 4) bn_relu_split4<F16, false>(v + 16 * hf + j, scv[4 * hf + j / 4], shv[4 * hf + j / 4], oh, ol, j / 4);
                     tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + A1_COL + b * 32 + 8 * hf, oh);
                     tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + A1_COL + b * 32 + 16 + 8 * hf, ol);
                 }

@@ -38,22 +38,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a lost TMA transaction or a descriptor fault must not hang the GPU (the box is
-// shared); after 2^22 failed probes (each sleeps up to 20 us in hardware) the kernel traps and the launch returns an error.
+// Bounded wait: a lost TMA transaction or a descriptor fault must not hang the GPU (the box is shared); after 2^20 failed probes
+// (a probe suspends the warp for a hardware-defined time, tens of cycles measured) the kernel traps and the launch returns an error.
+// A suspend-time hint on the probe was measured and changed nothing (4567 vs 4591 us per subject, within noise).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
-#ifdef UKBB_MBAR_HINT
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(20000u)     // suspend-time hint (ns): sleep in hardware instead of re-issuing the probe
-            : "memory");
-#else
         asm volatile(
             "{\n"
             ".reg .pred P1;\n"
@@ -63,7 +53,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-#endif
         if (!done && spins > (1u << 20)) {
 #ifdef UKBB_DEBUG_MBAR
             printf("mbar timeout: bar %x parity %u block %d thread %d\n", bar, parity, (int)blockIdx.x, (int)threadIdx.x);
@@ -321,8 +310,8 @@ __device__ __forceinline__ float2 unpack16t(uint32_t u) {
 }
 // split-operand ("x3") modes: a pair of FP32 values -> 16-bit hi pieces and 16-bit lo pieces, v ~ hi + lo with hi = rn16(v) and
 // lo = rn16(v - hi) (v - hi is exact in FP32).  FP16: hi is clamped to the finite range; inputs are >= 0 (post-ReLU) or small.
-// F8 (x2 scheme, FP16 only): `lo` receives [e4m3 pair of (a - hi) * 2^11 | e4m3 pair of hi << 16]; after the eight pairs of a 16-channel
-// group, x2_regroup() turns the eight words into the group layout [lo8 x 16 | hi8 x 16].
+// F8 (x2 scheme, FP16 only): `lo` receives [e4m3 pair of (a - hi) * 2^11 | e4m3 pair of hi << 16] (the kernels use split_pack4 below,
+// which writes the group layout [lo8 x 16 | hi8 x 16] directly).
 template <bool F16, bool F8 = false>
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
     if (F8) {
@@ -341,16 +330,42 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - __uint_as_float(hi & 0xffff0000u)), "f"(a - __uint_as_float(hi << 16)));
     }
 }
-// eight words [lo8 pair | hi8 pair << 16] (channel pairs 0..7 of a 16-channel group) -> [lo8 x 16 (4 words) | hi8 x 16 (4 words)]
-__device__ __forceinline__ void x2_regroup(uint32_t (&w)[8]) {
-    uint32_t r[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        r[k] = __byte_perm(w[2 * k], w[2 * k + 1], 0x5410);          // lo halves
-        r[4 + k] = __byte_perm(w[2 * k], w[2 * k + 1], 0x7632);      // hi halves
+// Four consecutive channels (quad q = 0..3 of a 16-channel group) -> the group's output words: oh[2q], oh[2q + 1] = the 16-bit hi pieces;
+// ol[2q], ol[2q + 1] = the 16-bit lo pieces, or (F8, x2 scheme) ol[q] = four e4m3 bytes of (x - hi) * 2^11 and ol[4 + q] = four e4m3 bytes
+// of hi, i.e. the eight words of a group are [lo8 x 16 | hi8 x 16] with no shuffle afterwards.  hi8 is converted from the packed FP16
+// pair (cvt.e4m3x2.f16x2), the scaling of the lo pieces is one packed multiply per pair.
+template <bool F16, bool F8>
+__device__ __forceinline__ void split_pack4(float a0, float a1, float a2, float a3, uint32_t* oh, uint32_t* ol, int q) {
+    if (F8) {
+        uint32_t h01, h23;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(a1), "f"(a0));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(a3), "f"(a2));
+        const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01)), f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+        uint64_t x01, x23, g01, g23, k;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x01) : "f"(a0), "f"(a1));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x23) : "f"(a2), "f"(a3));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(g01) : "f"(f01.x), "f"(f01.y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(g23) : "f"(f23.x), "f"(f23.y));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(k) : "f"(2048.f));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(x01) : "l"(x01), "l"(g01));                   // x - hi is exact in FP32, and so is * 2^11
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(x23) : "l"(x23), "l"(g23));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(x01) : "l"(x01), "l"(k));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(x23) : "l"(x23), "l"(k));
+        float l0, l1, l2, l3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(l0), "=f"(l1) : "l"(x01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(l2), "=f"(l3) : "l"(x23));
+        uint16_t p01, p23, q01, q23;
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p01) : "f"(l1), "f"(l0));
+        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p23) : "f"(l3), "f"(l2));
+        asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(q01) : "r"(h01));
+        asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(q23) : "r"(h23));
+        oh[2 * q] = h01; oh[2 * q + 1] = h23;
+        ol[q] = (uint32_t)p01 | ((uint32_t)p23 << 16);
+        ol[4 + q] = (uint32_t)q01 | ((uint32_t)q23 << 16);
+    } else {
+        split_pack<F16, false>(a0, a1, oh[2 * q], ol[2 * q]);
+        split_pack<F16, false>(a2, a3, oh[2 * q + 1], ol[2 * q + 1]);
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w[k] = r[k];
 }
 __device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {
     if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&u));

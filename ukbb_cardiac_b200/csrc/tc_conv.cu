@@ -183,14 +183,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
                     else if (F16) { a0 = fmaxf(a0, -65504.f); a1 = fmaxf(a1, -65504.f); a2 = fmaxf(a2, -65504.f); a3 = fmaxf(a3, -65504.f); }
                     if (SPLIT) {
-                        split_pack<F16, F8>(a0, a1, o[2 * j4], ol[2 * j4]);
-                        split_pack<F16, F8>(a2, a3, o[2 * j4 + 1], ol[2 * j4 + 1]);
+                        split_pack4<F16, F8>(a0, a1, a2, a3, o, ol, j4);
                     } else {
                         o[2 * j4] = pack16t<F16>(a0, a1);
                         o[2 * j4 + 1] = pack16t<F16>(a2, a3);
                     }
                 }
-                if (F8) x2_regroup(ol);
                 if (live) {
                     uint4* d4 = reinterpret_cast<uint4*>(dst + c);
                     d4[0] = make_uint4(o[0], o[1], o[2], o[3]);

@@ -448,7 +448,7 @@ int forward_tc(Engine* h, const float* image, int n, int x2, int y2, int x_pre, 
             fp.h = h2; fp.w4 = w2 / 4;
             fp.scale = P1.gp.scale; fp.shift = P1.gp.shift;
             memcpy(fp.shift0, S->c0_shift, sizeof(fp.shift0));
-            fp.out = P1.gp.out; fp.out_lo = P1.gp.out_lo;
+            fp.out = P1.gp.out; fp.out_lo = P1.gp.out_lo; fp.lo_n = P1.gp.lo_n;
             rc = launch_first(S, P1, map_img, fp, h->sms, st);
             if (rc) return rc;
             h->launches++;
