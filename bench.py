@@ -584,6 +584,26 @@ def run_c5(args):
     return 0
 
 
+def c4_parity(subject_dir: str, seqs):
+    """Label volumes written by deploy() for one subject (seg_sa / seg_la_2ch / seg4_la_4ch .nii.gz) against the CPU restatement of
+    the reference loop on the same input files."""
+    from oracle import fcn_oracle as fo
+    from ukbb_cardiac_b200 import nifti
+    out = {"tolerance": ">= 0.999 agreement, Dice >= 0.999 per class (north_star)", "sample": "subject 0, label files vs the float32 CPU restatement"}
+    worst_a, worst_d = 1.0, 1.0
+    for name, _, nc in seqs:
+        vol = nifti.load(os.path.join(subject_dir, name + ".nii.gz")).get_data()
+        seg = [f for f in ("seg_%s.nii.gz" % name, "seg4_%s.nii.gz" % name) if os.path.exists(os.path.join(subject_dir, f))][0]
+        lab = nifti.load(os.path.join(subject_dir, seg)).get_data()
+        _, _, _, pred = cpu_reference_sample(np.asarray(vol), nc, os.cpu_count() or 1)
+        a = float((np.asarray(lab) == pred).mean())
+        d = min(fo.categorical_dice(np.asarray(lab), pred, k) for k in range(nc))
+        out[name] = {"agreement": a, "min_dice": float(d)}
+        worst_a, worst_d = min(worst_a, a), min(worst_d, float(d))
+    out["agreement"], out["min_dice"] = worst_a, worst_d
+    return out
+
+
 def run_c4(args):
     """NIfTI in / NIfTI out: S synthetic subjects on local disk (sa + la_2ch + la_4ch .nii.gz each), three deploy() passes per step as
     demo_pipeline.py:63-64,89-96 runs deploy_network.py three times; outputs are deleted between steps (skip-if-exists would
@@ -648,6 +668,7 @@ def run_c4(args):
         torch.cuda.synchronize(dev)
 
     warm = max(args.warmup, 1)
+    parity = None
     try:
         for _ in range(warm):
             step(); clean()
@@ -669,6 +690,8 @@ def run_c4(args):
                 dt = float(t.item())
             secs += dt
             out_bytes = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(root) for f in fs) - in_bytes
+            if _ == args.steps - 1 and rank == 0 and world == 1 and args.cpu_frames > 0:
+                parity = c4_parity(os.path.join(root, "subj000"), seqs)       # the label FILES of subject 0 vs the CPU restatement
             clean()
         sampler.stop_flag.set()
         sampler.join(timeout=3)
@@ -690,7 +713,7 @@ def run_c4(args):
                     "d2h_bytes_per_step": S * (np.prod(SA) + 2 * np.prod(LA)).item(), "file_bytes_in_per_step": in_bytes, "file_bytes_out_per_step": out_bytes},
             "host_stage_seconds": {k: round(v, 3) for k, v in sorted(stages.items())},
             "host_stage_bound": max(stages, key=stages.get) if stages else None,
-            "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "clocks": sampler.summary(),
+            "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "parity": parity, "clocks": sampler.summary(),
         }
         print(json.dumps(line))
     if world > 1:

@@ -1,6 +1,6 @@
 #!/bin/bash
-# perf visit: short bench + per-subject launch list (ncu gpu__time_duration) for MODE (default fp16x3)
-MODE=${MODE:-fp16x3}
+# perf visit: short bench + per-subject launch list (ncu gpu__time_duration) for MODE (default fp16x2)
+MODE=${MODE:-fp16x2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
 timeout 600 python bench.py --mode $MODE --subjects ${SUBJ:-16} --steps 2 --warmup 3 --cpu-frames ${CPUF:-0} > gpurun_out/bench_$MODE.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench_$MODE.json

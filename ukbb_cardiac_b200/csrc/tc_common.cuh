@@ -40,7 +40,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Bounded wait: a lost TMA transaction or a descriptor fault must not hang the GPU (the box is shared); after 2^20 failed probes
 // (a probe suspends the warp for a hardware-defined time, tens of cycles measured) the kernel traps and the launch returns an error.
-// A suspend-time hint on the probe was measured and changed nothing (4567 vs 4591 us per subject, within noise).
+// A suspend-time hint on the probe and a __nanosleep(32 / 128 ns) back-off after a failed probe were measured and changed nothing
+// (4567 / 4599 / 4594 vs 4591 us per subject): a third of the head's issued instructions are probes, but the busy warps are bound
+// by their own dependency chains, not by issue slots.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
@@ -324,7 +326,13 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
     } else if (F16) {
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
         const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - h.y), "f"(a - h.x));
+        uint64_t x, hh;
+        float l0, l1;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(hh) : "f"(h.x), "f"(h.y));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(hh));                       // one packed subtract for the pair
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(l0), "=f"(l1) : "l"(x));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l1), "f"(l0));
     } else {
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - __uint_as_float(hi & 0xffff0000u)), "f"(a - __uint_as_float(hi << 16)));
