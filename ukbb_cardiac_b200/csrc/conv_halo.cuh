@@ -39,18 +39,24 @@ struct ConvHaloParams {
 // F8 (x2 scheme, tc_common.cuh): the chunks of a tile are walked TWICE -- lo planes first (patch + weight tiles holding FP8 correction
 // operands, kind::f8f6f4), then the hi planes (kind::f16; the first instruction of each sub-tile rescales its accumulator) -- so a patch stage
 // holds one plane and the weight stream is one tile per (pass, chunk, tap).
-template <int CC, int COUT, bool RESIDENT, int NKB /* 9 * chunks when RESIDENT */, bool SPLIT = false, bool F8 = false>
+// PAIR (x2 scheme only): the two CTAs of a cluster execute every UMMA together (tcgen05 cta_group::2, M = 256 = sub-tile h of both CTAs'
+// tiles): each CTA keeps only ITS half of the Cout rows of a weight tile, so an instruction reads 4 KB of A + Cout/2 * 32 B of B per
+// CTA instead of 4 KB + Cout * 32 B -- the shared-memory operand port, not the tensor pipe, bounds these layers.
+// The leader CTA issues all UMMAs and commits; the loads of both CTAs signal the leader's barriers; the peer's MMA warp is idle.
+template <int CC, int COUT, bool RESIDENT, int NKB /* 9 * chunks when RESIDENT */, bool SPLIT = false, bool F8 = false, bool PAIR = false>
 struct ConvHaloCfg {
     static_assert(!SPLIT || !RESIDENT, "the split variant streams its weights");
     static_assert(!F8 || SPLIT, "the FP8 correction scheme is a split-operand scheme");
+    static_assert(!PAIR || F8, "the CTA-pair variant exists for the x2 scheme");
     static constexpr int RB = CC * 2;                                   // bytes per patch row (pixel)
     static constexpr int PLANE_BYTES = (324 * RB + 1023) / 1024 * 1024;
     static constexpr int PATCH_BYTES = ((SPLIT && !F8) ? 2 : 1) * PLANE_BYTES;
-    static constexpr int B_TILE = (COUT * RB + 1023) / 1024 * 1024;
+    static constexpr int B_ROWS = PAIR ? COUT / 2 : COUT;                // weight rows held by one CTA
+    static constexpr int B_TILE = (B_ROWS * RB + 1023) / 1024 * 1024;
     // streamed weights: the ring must cover the ~2000-cycle latency of an L2 fetch -- with four 16 KB stages (512 cycles of UMMAs
     // each) the tensor pipe waited for weights half of the time (7350 cycles per chunk for 3456 cycles of UMMAs); two patch stages
     // leave room for eight weight stages (Cout = 128) / four 32 KB stages (Cout = 256)
-    static constexpr int A_STREAM = 2;
+    static constexpr int A_STREAM = PAIR ? 4 : 2;
     static constexpr int B_FIT = (222 * 1024 - A_STREAM * PATCH_BYTES) / B_TILE;
     static constexpr int B_TILES = RESIDENT ? NKB : (B_FIT > 8 ? 8 : B_FIT);
     static constexpr int B_BYTES = B_TILES * B_TILE;
@@ -70,12 +76,13 @@ struct ConvHaloCfg {
 // multicast that lands at the same shared-memory offset in both CTAs and signals both b_full barriers -- and a ring slot is refilled
 // only after BOTH tensor pipes have consumed it (tcgen05.commit multicast on both b_empty barriers, count 2).  The level-3/4 layers
 // stream 0.29 / 1.18 MB of weights per 16x16-pixel tile and ran at the L2 roofline (6.7 TB/s of L2 reads).
-template <int CC, int COUT, bool RESIDENT, int NKB, bool F16, bool CL = false, bool SPLIT = false, bool F8 = false>
+template <int CC, int COUT, bool RESIDENT, int NKB, bool F16, bool CL = false, bool SPLIT = false, bool F8 = false, bool PAIR = false>
 __global__ void __launch_bounds__(256, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const ConvHaloParams p) {
     using namespace tc;
-    using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB, SPLIT, F8>;
+    using Cfg = ConvHaloCfg<CC, COUT, RESIDENT, NKB, SPLIT, F8, PAIR>;
+    static_assert(!PAIR || CL, "CTA pairs are clusters of two");
     constexpr bool X3 = SPLIT && !F8;
     const int n_chunk_steps = F8 ? 2 * p.chunks : p.chunks;     // x2: [0, chunks) = lo planes, [chunks, 2 chunks) = hi planes
     constexpr int RB = Cfg::RB, AST = Cfg::A_STAGES, BST = Cfg::B_TILES, ACC = Cfg::ACC_STAGES;
@@ -102,12 +109,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < AST; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < 8; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), CL ? 2 : 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+        for (int s = 0; s < 8; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), (CL && !PAIR) ? 2 : 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), PAIR ? 8 : 4); }   // PAIR: the leader's barrier, both epilogues
         mbar_init(wfull, 1);
         fence_barrier_init();
     }
-    if (warp == 2) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+    if (warp == 2) {
+        if (PAIR) { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+    }
     if (warp == 3) {
         float* ss = const_cast<float*>(s_scale);
         for (int c = lane; c < COUT; c += 32) { ss[c] = p.scale[c]; ss[COUT + c] = p.shift[c]; }
@@ -152,14 +162,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int ch = (F8 && cs >= p.chunks) ? cs - p.chunks : cs;
                     const bool lo_pass = F8 && cs < p.chunks;
                     mbar_wait(a_empty(as), aph ^ 1);
+                    if (PAIR) {                              // both patches complete on the leader's barrier
+                        if (crank == 0) mbar_arrive_expect_tx(a_full(as), 2 * 324 * RB);
+                        tma_load_4d_pair(smem_base + as * Cfg::PATCH_BYTES, &map_a, mapa_rank(a_full(as), 0), ch * CC, x0 - 1, y0 - 1, (lo_pass ? p.lo_n : 0) + n);
+                    } else {
                     mbar_arrive_expect_tx(a_full(as), (X3 ? 2 : 1) * 324 * RB);
                     tma_load_4d(smem_base + as * Cfg::PATCH_BYTES, &map_a, a_full(as), ch * CC, x0 - 1, y0 - 1, (lo_pass ? p.lo_n : 0) + n);
+                    }
                     if (X3) tma_load_4d(smem_base + as * Cfg::PATCH_BYTES + Cfg::PLANE_BYTES, &map_a, a_full(as), ch * CC, x0 - 1, y0 - 1, p.lo_n + n);
                     if (++as == AST) { as = 0; aph ^= 1; }
                     if (!RESIDENT) {
                         for (int tap = 0; tap < (X3 ? 18 : 9); ++tap) {         // x3: (tap, hi), (tap, lo), ... ; lo tiles are rows [COUT, 2 COUT) of the weight map
                             const int tp = X3 ? tap >> 1 : tap, wrow = X3 ? (tap & 1) * COUT : (lo_pass ? COUT : 0);
                             mbar_wait(b_empty(bs), bph ^ 1);
+                            if (PAIR) {                      // this CTA's half of the rows (the weight map's box is Cout / 2 rows)
+                                if (crank == 0) mbar_arrive_expect_tx(b_full(bs), COUT * RB);
+                                tma_load_2d_pair(b_base + bs * Cfg::B_TILE, &map_b, mapa_rank(b_full(bs), 0), tp * p.cin + ch * CC, wrow + (int)crank * (COUT / 2));
+                                ++bt;
+                                if (++bs == BST) { bs = 0; bph ^= 1; }
+                                continue;
+                            }
                             mbar_arrive_expect_tx(b_full(bs), COUT * RB);
                             if (!CL) tma_load_2d(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tp * p.cin + ch * CC, wrow);
                             else if ((uint32_t)(bt & 1) == crank) tma_load_2d_mc(b_base + bs * Cfg::B_TILE, &map_b, b_full(bs), tp * p.cin + ch * CC, wrow, (uint16_t)3);
@@ -184,6 +206,53 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (RESIDENT) { mbar_wait(wfull, 0); tc_fence_after(); }
         int as = 0, bs = 0, acc = 0;
         uint32_t aph = 0, bph = 0, acc_ph = 0;
+        if (PAIR) {
+            // ---- CTA pair: the leader issues M = 256 UMMAs over its own and the peer's sub-tile h; the peer's MMA warp has nothing to do
+            const uint32_t idesc_p = make_idesc_f16(256, COUT), idesc8_p = make_idesc_e4m3(256, COUT);
+            if (crank == 0)
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+                mbar_wait(tempty(acc), acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + acc * (2 * COUT);
+                // right sub-tiles: needed if either tile of the pair has one (the other CTA then computes on zero-filled patch rows)
+                const int nh = (((tile / tiles_per_tx) * 16 + 8 < p.wo) || (((tile + 1) / tiles_per_tx) * 16 + 8 < p.wo)) ? 2 : 1;
+                for (int ch = 0; ch < n_chunk_steps; ++ch) {
+                    const bool lo_pass = ch < p.chunks;
+                    const bool first_main = ch == p.chunks;
+                    mbar_wait(a_full(as), aph);
+                    tc_fence_after();
+                    const uint32_t a_lo = (((smem_base + as * Cfg::PATCH_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(b_full(bs), bph);
+                        tc_fence_after();
+                        const uint32_t b_lo = (((b_base + bs * Cfg::B_TILE) & 0x3FFFF) >> 4) | (1u << 16);
+                        const uint32_t w_lo = a_lo + ((((tap / 3) * 18 + (tap % 3)) * RB) >> 4);
+                        if (leader) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                if (h < nh)
+#pragma unroll
+                                for (int k = 0; k < CC / 16; ++k) {
+                                    if (lo_pass) umma_pair_lohi<1>(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi, idesc8_p,
+                                                                   (ch | tap | k) != 0 ? 1u : 0u);
+                                    else if (first_main && tap == 0 && k == 0) umma_pair_lohi<2>(d0 + h * COUT, w_lo + ((8 * h * RB) >> 4), a_hi, b_lo, b_hi, idesc_p, 1u);
+                                    else umma_pair_lohi<0>(d0 + h * COUT, w_lo + ((8 * h * RB + k * 32) >> 4), a_hi, b_lo + ((k * 32) >> 4), b_hi, idesc_p, 1u);
+                                }
+                            umma_commit_pair(b_empty(bs), (uint16_t)3);
+                        }
+                        __syncwarp();
+                        if (++bs == BST) { bs = 0; bph ^= 1; }
+                    }
+                    if (leader) umma_commit_pair(a_empty(as), (uint16_t)3);
+                    __syncwarp();
+                    if (++as == AST) { as = 0; aph ^= 1; }
+                }
+                if (leader) umma_commit_pair(tfull(acc), (uint16_t)3);
+                __syncwarp();
+                if (++acc == ACC) { acc = 0; acc_ph ^= 1; }
+            }
+        } else
         for (int tile = tile_first; tile < tile_end; tile += tile_step) {
             mbar_wait(tempty(acc), acc_ph ^ 1);
             tc_fence_after();
@@ -352,7 +421,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty(acc));
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(mapa_rank(tempty(acc), 0));    // the leader's barrier counts both epilogues
+                else mbar_arrive(tempty(acc));
+            }
             if (++acc == ACC) { acc = 0; acc_ph ^= 1; }
         }
     }
@@ -361,7 +433,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (CL) cluster_sync();                              // the peer may still multicast into this CTA's ring / arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

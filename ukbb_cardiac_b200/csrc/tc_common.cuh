@@ -108,6 +108,66 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
                  : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (tcgen05 cta_group::2)
+// Two CTAs of a cluster execute ONE tcgen05.mma with M = 256: each CTA supplies its own 128 rows of A and HALF of the N rows of B
+// from the same shared-memory offsets, and receives its 128 accumulator rows in its own tensor memory.  The leader (cluster rank 0)
+// issues; TMA loads of both CTAs signal the LEADER's mbarrier (its shared::cluster address), tcgen05.commit multicasts to both.
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// kind: 0 = kind::f16 accumulate / overwrite, 1 = kind::f8f6f4, 2 = kind::f16 with D <- A.B + D * 2^-15
+template <int KIND>
+__device__ __forceinline__ void umma_pair_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == 2) {
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, 1, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p, 15;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+    } else if (KIND == 1) {
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc),
+            "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc),
+            "r"(accumulate)
+            : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

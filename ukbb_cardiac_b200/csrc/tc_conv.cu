@@ -239,17 +239,17 @@ static int launch_tc_x3(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st
 }
 
 // levels 3 / 4: streamed weights, clusters of two CTAs share every weight tile through TMA multicast (conv_halo.cuh)
-template <int CC, int COUT, bool F16, bool SPLIT, bool F8 = false>
+template <int CC, int COUT, bool F16, bool SPLIT, bool F8 = false, bool PAIR = false>
 static int launch_halo2(const TcLayerPlan& P, int sms, cudaStream_t st) {
-    using Cfg = ConvHaloCfg<CC, COUT, false, 0, SPLIT, F8>;
+    using Cfg = ConvHaloCfg<CC, COUT, false, 0, SPLIT, F8, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
-        UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT, F8, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int pairs = (P.hp.n_tiles + 1) / 2;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
-    UKBB_CUDA(launch_pdl<2>(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT, F8>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.hp));
+    UKBB_CUDA(launch_pdl<2>(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT, F8, PAIR>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.hp));
     return UKBB_OK;
 }
 template <int CC, int COUT, bool SPLIT>
@@ -281,8 +281,8 @@ int launch_plan(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st) {
             GCASE(16, 16, 1); GCASE(32, 32, 1); GCASE(64, 64, 1); GCASE(16, 32, 2); GCASE(32, 64, 2);
 #undef GCASE
         } else if (P.kind == 1) {
-            if (P.cc == 32 && P.cout == 128) return launch_halo2<32, 128, true, true, true>(P, sms, st);
-            if (P.cc == 32 && P.cout == 256) return launch_halo2<32, 256, true, true, true>(P, sms, st);
+            if (P.pair && P.cc == 32 && P.cout == 128) return launch_halo2<32, 128, true, true, true, true>(P, sms, st);
+            if (P.pair && P.cc == 32 && P.cout == 256) return launch_halo2<32, 256, true, true, true, true>(P, sms, st);
         } else {
             if (P.cc == 64 && P.cout == 128) return launch_tc2<64, 128, true, true, true>(P, sms, st);
             if (P.cc == 64 && P.cout == 256) return launch_tc2<64, 256, true, true, true>(P, sms, st);

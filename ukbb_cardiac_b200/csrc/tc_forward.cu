@@ -150,11 +150,12 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
         cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
         UKBB_ENCODE("activation", &P.map_a, dt16, 4, (void*)in, dims, strides, box, estr);
     }
+    P.pair = (P.kind == 1 && S->f8) ? 1 : 0;        // x2: the 128- / 256-channel halo layers run as CTA pairs, half of the weight rows per CTA
     {   // weights [planes * cout][taps * cin]: the lo plane = rows [cout, 2 cout)
         const int ktot = p.taps * L.cin;
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(planes * L.cout)};
         cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-        cuuint32_t box[2] = {(cuuint32_t)cc, (cuuint32_t)L.cout};
+        cuuint32_t box[2] = {(cuuint32_t)cc, (cuuint32_t)(P.pair ? L.cout / 2 : L.cout)};
         UKBB_ENCODE("weights", &P.map_b, dt16, 2, (void*)S->w[li], dims, strides, box, e2);
     }
     P.valid = true;

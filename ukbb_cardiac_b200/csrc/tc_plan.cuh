@@ -44,6 +44,7 @@ struct TcLayerPlan {
                                     // 2 = pixel-group rows (conv_group_kernel)
     int split = 0;
     int f8 = 0;                     // split scheme with FP8 correction operands in the lo planes (UKBB_MODE_FP16X2)
+    int pair = 0;                   // conv_halo as CTA pairs (tcgen05 cta_group::2): the weight map's box holds Cout / 2 rows
     bool valid = false;
 };
 
