@@ -48,23 +48,29 @@ struct ConvGroupParams {
 // instance holds 144 KB of weights and fits two (hi, lo) patch stages only with 14-row tiles.
 // F8 (x2 scheme, tc_common.cuh): the lo planes hold FP8 correction operands; per K-slice ONE kind::f8f6f4 UMMA (A_lo8 . B_lo8) replaces the
 // two correction products, all of them are issued before the FP16 pass whose first instruction rescales the accumulator.
-template <int CC, int COUT, int STRIDE, bool SPLIT = false, bool F8 = false>
+// PAIR (x2 scheme): clusters of two CTAs execute every UMMA together (tcgen05 cta_group::2, M = 256 = both CTAs' tiles): a CTA keeps
+// only ITS 32 of the 64 rows of every weight tile, so an instruction reads 4 KB of A + 1 KB of B per CTA instead of 4 + 2 KB (these N = 64
+// UMMAs are bound by the shared-memory operand port: 48 cycles for 32 cycles of tensor work), and the resident weights take half the
+// shared memory -- the 64 -> 64 instance gets its 16-row tiles and the staging tiles back.  Protocol as in conv_halo.cuh.
+template <int CC, int COUT, int STRIDE, bool SPLIT = false, bool F8 = false, bool PAIR = false>
 struct ConvGroupCfg {
     static_assert(!F8 || SPLIT, "the FP8 correction scheme is a split-operand scheme");
+    static_assert(!PAIR || F8, "the CTA-pair variant exists for the x2 scheme");
     static constexpr bool MERGE = SPLIT && !F8;                // x3: [w_hi ; w_lo] tiles, N = 128 UMMAs, two accumulator column blocks
     static constexpr int G = 64 / CC;                          // input pixels per 128-byte row
     static constexpr int GOUT = STRIDE == 1 ? G : G / 2;       // output pixels per UMMA row
     static constexpr int N = GOUT * COUT;
     static constexpr int J = STRIDE == 1 ? G + 2 : G + 1;      // K-slices per kernel row
     static constexpr int KS = CC / 16;
-    static constexpr int TROWS = (SPLIT && CC == 64 && STRIDE == 1) ? 14 : 16;
+    static constexpr int TROWS = (SPLIT && CC == 64 && STRIDE == 1 && !PAIR) ? 14 : 16;
     static constexpr int PU = STRIDE == 1 ? 10 : 9;            // patch groups per row
     static constexpr int PR = STRIDE == 1 ? TROWS + 2 : 2 * TROWS + 1;   // patch rows
     static constexpr int PATCH_TX = PR * PU * 128;
     static constexpr int PATCH_BYTES = (PATCH_TX + 1023) / 1024 * 1024;
     static constexpr int A_STAGE_BYTES = (SPLIT ? 2 : 1) * PATCH_BYTES;   // hi patch | lo patch
     static constexpr int B_ROW = CC * 2;
-    static constexpr int B_TILE = (N * B_ROW + 1023) / 1024 * 1024;
+    static constexpr int B_ROWS = PAIR ? N / 2 : N;            // weight rows of a tile held by one CTA
+    static constexpr int B_TILE = (B_ROWS * B_ROW + 1023) / 1024 * 1024;
     static constexpr int NB_TILES = 3 * J;
     static constexpr int B_SET = NB_TILES * B_TILE;
     static constexpr int B_BYTES = (SPLIT ? 2 : 1) * B_SET;    // hi tiles | lo tiles
@@ -175,12 +181,12 @@ struct TileWalk {
     }
 };
 
-template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT = false, bool F8 = false>
+template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT = false, bool F8 = false, bool PAIR = false>
 __global__ void __launch_bounds__(256, 1)
 conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_out, const ConvGroupParams p) {
     using namespace tc;
-    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT, F8>;
+    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT, F8, PAIR>;
     constexpr bool MERGE = Cfg::MERGE;
     constexpr int AST = Cfg::A_STAGES, G = Cfg::G, J = Cfg::J, KS = Cfg::KS, PU = Cfg::PU, N = Cfg::N, TROWS = Cfg::TROWS;
     griddep_launch();
@@ -204,11 +210,14 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_out); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < AST; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), PAIR ? 8 : 4); }   // PAIR: the leader's barrier, both epilogues
         mbar_init(wfull, 1);
         fence_barrier_init();
     }
-    if (warp == 2) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+    if (warp == 2) {
+        if (PAIR) { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+    }
     if (warp == 3) {
         for (int c = lane; c < N; c += 32) { s_scale[c] = p.scale[c % COUT]; s_shift[c] = p.shift[c % COUT]; }
     }
@@ -218,27 +227,50 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (warp != 0) griddep_wait();                       // the producer waits after it has issued the weight loads
-    const int my_tiles = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // tile walk: round-robin over CTAs, or (PAIR) pairs of tiles (2 k, 2 k + 1) round-robin over clusters; with an odd tile count the
+    // peer of the last pair walks a tile beyond the tensor (its loads are harmless, its epilogue stores nothing)
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const int n_slices = p.n_tiles / (p.tiles_x * p.tiles_y);
+    const int walk_first = PAIR ? 2 * ((int)blockIdx.x >> 1) + (int)crank : (int)blockIdx.x;
+    const int walk_step = PAIR ? ((int)gridDim.x >> 1) * 2 : (int)gridDim.x;
+    const int n_units = PAIR ? (p.n_tiles + 1) >> 1 : p.n_tiles, unit0 = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x, unit_step = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
+    const int my_tiles = unit0 < n_units ? (n_units - unit0 + unit_step - 1) / unit_step : 0;
+    if (PAIR) cluster_sync();                            // both CTAs' barriers are initialised before any remote arrive / commit
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            if (PAIR) {                                  // this CTA's 32 rows of every tile (box of the weight map: 32 rows); all on the leader's barrier
+                if (crank == 0) mbar_arrive_expect_tx(wfull, 2 * Cfg::NB_TILES * N * Cfg::B_ROW);
+                for (int t = 0; t < 2 * Cfg::NB_TILES; ++t)
+                    tma_load_2d_pair(b_base + t * Cfg::B_TILE, &map_b, mapa_rank(wfull, 0), 0, t * N + (int)crank * (N / 2));
+            } else {
             mbar_arrive_expect_tx(wfull, (SPLIT ? 2 : 1) * Cfg::NB_TILES * N * Cfg::B_ROW);
             for (int t = 0; t < (SPLIT ? 2 : 1) * Cfg::NB_TILES; ++t) {
                 // global: hi tiles, then lo tiles.  Shared (SPLIT): tile t = [hi 64 rows | lo 64 rows], one N = 128 B operand
                 const int tt = t % Cfg::NB_TILES, pl = t / Cfg::NB_TILES;
                 tma_load_2d(b_base + (MERGE ? tt * 2 * Cfg::B_TILE + pl * Cfg::B_TILE : t * Cfg::B_TILE), &map_b, wfull, 0, t * N);
             }
+            }
             griddep_wait();
             TileWalk w;
-            w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+            w.init(walk_first, walk_step, p.tiles_x, p.tiles_y);
             int as = 0;
             uint32_t aph = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 mbar_wait(a_empty(as), aph ^ 1);
-                mbar_arrive_expect_tx(a_full(as), (SPLIT ? 2 : 1) * Cfg::PATCH_TX);
                 const uint32_t dst = smem_base + as * Cfg::A_STAGE_BYTES;
                 const int cx = STRIDE == 1 ? w.tx * 8 - 1 : w.tx * 8, cy = STRIDE == 1 ? w.ty * TROWS - 1 : w.ty * 2 * TROWS;
+                if (PAIR) {                              // the patches of both CTAs complete on the leader's barrier
+                    if (crank == 0) mbar_arrive_expect_tx(a_full(as), 4 * Cfg::PATCH_TX);
+                    const uint32_t lbar = mapa_rank(a_full(as), 0);
+                    tma_load_4d_pair(dst, &map_a, lbar, 0, cx, cy, w.n);
+                    tma_load_4d_pair(dst + Cfg::PATCH_BYTES, &map_a, lbar, 0, cx, cy, p.lo_n + w.n);
+                    if (++as == AST) { as = 0; aph ^= 1; }
+                    w.next();
+                    continue;
+                }
+                mbar_arrive_expect_tx(a_full(as), (SPLIT ? 2 : 1) * Cfg::PATCH_TX);
                 tma_load_4d(dst, &map_a, a_full(as), 0, cx, cy, w.n);
                 if (SPLIT) tma_load_4d(dst + Cfg::PATCH_BYTES, &map_a, a_full(as), 0, cx, cy, p.lo_n + w.n);
                 if (++as == AST) { as = 0; aph ^= 1; }
@@ -255,10 +287,51 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         constexpr uint32_t a_hi = (uint32_t)(((STRIDE == 1 ? PU : 2 * PU) * 128) >> 4) | (1u << 14) | (2u << 29);
         constexpr uint32_t b_hi = (uint32_t)((8 * Cfg::B_ROW) >> 4) | (1u << 14) | (blayout << 29);
         const uint32_t b_lo = ((b_base & 0x3FFFF) >> 4) | (1u << 16);
-        mbar_wait(wfull, 0);
-        tc_fence_after();
         int as = 0, acc = 0;
         uint32_t aph = 0, acc_ph = 0;
+        if (PAIR) {
+            // ---- CTA pair: the leader issues M = 256 UMMAs over both CTAs' tiles; the peer's MMA warp has nothing to do
+            const uint32_t idesc_p = make_idesc_f16(256, N), idesc8_p = make_idesc_e4m3(256, N);
+            if (crank == 0) {
+                mbar_wait(wfull, 0);
+                tc_fence_after();
+                for (int i = 0; i < my_tiles; ++i) {
+                    mbar_wait(tempty(acc), acc_ph ^ 1);
+                    mbar_wait(a_full(as), aph);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + acc * Cfg::ACC_COLS;
+                    const uint32_t a_lo = (((smem_base + as * Cfg::A_STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+                    if (leader) {
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int j = 0; j < J; ++j) {
+                                const int jj = STRIDE == 1 ? j - 1 : j;
+                                const int ro = jj < 0 ? -1 : jj / G;
+                                const int sub = jj - ro * G;
+                                const int arow = STRIDE == 1 ? ky * PU + 1 + ro : ky * PU + ro;
+#pragma unroll
+                                for (int ks = 0; ks < KS; ++ks) {
+                                    const uint32_t ao = (uint32_t)((arow * 128 + sub * CC * 2 + ks * 32) >> 4);
+                                    const uint32_t bo = (uint32_t)(((ky * J + j) * Cfg::B_TILE + ks * 32) >> 4);
+                                    if (pass == 0) umma_pair_lohi<1>(d, a_lo + (Cfg::PATCH_BYTES >> 4) + ao, a_hi, b_lo + (Cfg::B_SET >> 4) + bo, b_hi, idesc8_p, (ky | j | ks) != 0 ? 1u : 0u);
+                                    else if ((ky | j | ks) == 0) umma_pair_lohi<2>(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc_p, 1u);
+                                    else umma_pair_lohi<0>(d, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc_p, 1u);
+                                }
+                            }
+                        umma_commit_pair(a_empty(as), (uint16_t)3);
+                        umma_commit_pair(tfull(acc), (uint16_t)3);
+                    }
+                    __syncwarp();
+                    if (++as == AST) { as = 0; aph ^= 1; }
+                    if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                }
+            }
+        } else {
+        mbar_wait(wfull, 0);
+        tc_fence_after();
         for (int i = 0; i < my_tiles; ++i) {
             mbar_wait(tempty(acc), acc_ph ^ 1);
             mbar_wait(a_full(as), aph);
@@ -300,13 +373,14 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (++as == AST) { as = 0; aph ^= 1; }
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp - 4;
         const int r = q * 32 + lane;                         // TMEM lane = tile row * 8 + group
         const bool issuer = threadIdx.x == 128;
         TileWalk w;
-        w.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+        w.init(walk_first, walk_step, p.tiles_x, p.tiles_y);
         int acc = 0;
         uint32_t acc_ph = 0;
         // folded BN of the COUT channels in registers (SPLIT): two broadcast LDS.128 per four outputs were a tenth of the epilogue
@@ -323,7 +397,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 // acc = columns [0, 64) + columns [64, 128) (x3); hi / lo pieces, 128 contiguous bytes each per thread (this row's group):
                 // four 256-bit stores per plane, or (STAGED) swizzled staging tiles and two TMA stores
                 const int row = r >> 3, y = w.ty * TROWS + row, gx = w.tx * 8 + (r & 7);
-                const bool live = row < TROWS && y < p.ho && gx < p.wog;
+                const bool live = row < TROWS && y < p.ho && gx < p.wog && w.n < n_slices;
                 uint32_t* dst = p.out + (((size_t)w.n * p.ho + y) * p.wog + gx) * 32;
                 const uint32_t srow = out_base + r * 128;
 #pragma unroll
@@ -335,7 +409,10 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (c8 == 3) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty(acc));     // accumulator is in registers: release it to the MMA warp
+                        if (lane == 0) {                             // accumulator is in registers: release it to the MMA warp
+                            if (PAIR) mbar_arrive_cluster(mapa_rank(tempty(acc), 0));
+                            else mbar_arrive(tempty(acc));
+                        }
                     }
                     if (MERGE) {
 #pragma unroll
@@ -364,7 +441,7 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (Cfg::STAGED) {
                     fence_proxy_async();
                     named_bar_sync(1, 128);
-                    if (issuer) {
+                    if (issuer && w.n < n_slices) {
                         tma_store_4d(&map_out, out_base, 0, w.tx * 8, w.ty * TROWS, w.n);
                         tma_store_4d(&map_out, out_base + Cfg::OUT_BYTES, 0, w.tx * 8, w.ty * TROWS, w.n + p.lo_n);
                         bulk_commit();
@@ -412,9 +489,11 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync();                            // the peer may still arrive on this CTA's barriers / read its shared memory
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

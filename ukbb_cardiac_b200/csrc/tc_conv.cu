@@ -257,16 +257,22 @@ static int launch_halo(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st)
     return fp16 ? launch_halo2<CC, COUT, true, SPLIT>(P, sms, st) : launch_halo2<CC, COUT, false, SPLIT>(P, sms, st);
 }
 
-template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT, bool F8 = false>
+template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT, bool F8 = false, bool PAIR = false>
 static int launch_group2(const TcLayerPlan& P, int sms, cudaStream_t st) {
-    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT, F8>;
+    using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT, F8, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
-        UKBB_CUDA(cudaFuncSetAttribute(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        UKBB_CUDA(cudaFuncSetAttribute(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT, F8, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
+    if (PAIR) {                      // clusters of two CTAs, a pair of tiles per cluster and round
+        const int pairs = (P.gp.n_tiles + 1) / 2;
+        const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+        UKBB_CUDA(launch_pdl<2>(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT, F8, PAIR>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.map_out, P.gp));
+        return UKBB_OK;
+    }
     const int grid = P.gp.n_tiles < sms ? P.gp.n_tiles : sms;
-    UKBB_CUDA(launch_pdl(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT, F8>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.map_out, P.gp));
+    UKBB_CUDA(launch_pdl(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT, F8, PAIR>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.map_out, P.gp));
     return UKBB_OK;
 }
 template <int CC, int COUT, int STRIDE, bool SPLIT>
@@ -277,8 +283,9 @@ static int launch_group(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st
 int launch_plan(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st) {
     if (P.f8) {                     // x2 scheme (FP16 pieces + FP8 corrections): same plans and tile shapes as the x3 instances
         if (P.kind == 2) {
-#define GCASE(CIN, COUTV, S) if (P.p.cin == CIN && P.cout == COUTV && P.p.stride == S) return launch_group2<CIN, COUTV, S, true, true, true>(P, sms, st)
-            GCASE(16, 16, 1); GCASE(32, 32, 1); GCASE(64, 64, 1); GCASE(16, 32, 2); GCASE(32, 64, 2);
+            if (P.pair && P.p.cin == 64 && P.cout == 64 && P.p.stride == 1) return launch_group2<64, 64, 1, true, true, true, true>(P, sms, st);
+#define GCASE(CIN, COUTV, S) if (!P.pair && P.p.cin == CIN && P.cout == COUTV && P.p.stride == S) return launch_group2<CIN, COUTV, S, true, true, true>(P, sms, st)
+            GCASE(16, 16, 1); GCASE(32, 32, 1); GCASE(16, 32, 2); GCASE(32, 64, 2);
 #undef GCASE
         } else if (P.kind == 1) {
             if (P.pair && P.cc == 32 && P.cout == 128) return launch_halo2<32, 128, true, true, true, true>(P, sms, st);

@@ -82,6 +82,10 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     P.kind = (ks == 3 && L.cin <= 64 && S->wg[li] && wi % (64 / L.cin) == 0) ? 2 : (ks == 3 && s == 1 && L.cin >= 128) ? 1 : 0;
     const int cc = (P.kind == 1 && split) ? 32 : chunk_for(L.cin);
     P.cc = cc;
+    // x2: the halo layers and the pixel-group layers run as CTA pairs (tcgen05 cta_group::2), half of the weight rows of a tile per CTA
+    // Of the pixel-group layers only 64 -> 64 gains (206 -> 168 us: it is bound by the operand port and its weights filled the shared
+    // memory); the HBM-bound 16 -> 32, 32 -> 32 and 32 -> 64 instances lose 30-40 % when two CTAs advance in lockstep (measured).
+    P.pair = (S->f8 && (P.kind == 1 || (P.kind == 2 && L.cin == 64))) ? 1 : 0;
     // output box of the per-tap kernel: bw | wo, bh | ho by construction (padded sizes are multiples of 16 at level 0)
     int bw = 16 >> level_out; if (bw < 1) bw = 1;
     int bh = 8; while (bh > 1 && (ho % bh != 0 || bw * bh > 128)) bh >>= 1;
@@ -100,7 +104,7 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
     const cuuint64_t n_dim = (cuuint64_t)planes * nb;               // the lo plane = slices [nb, 2 nb)
     if (P.kind == 2) {
         const int g = 64 / L.cin, gout = s == 1 ? g : g / 2;
-        const int trows = (split && L.cin == 64 && s == 1) ? 14 : 16;   // ConvGroupCfg::TROWS
+        const int trows = (split && L.cin == 64 && s == 1 && !P.pair) ? 14 : 16;   // ConvGroupCfg::TROWS
         const int pu = s == 1 ? 10 : 9, pr = s == 1 ? trows + 2 : 2 * trows + 1, jn = s == 1 ? g + 2 : g + 1;
         ConvGroupParams& gp = P.gp;
         gp.tiles_x = (wo / gout + 7) / 8; gp.tiles_y = (ho + trows - 1) / trows; gp.n_tiles = gp.tiles_x * gp.tiles_y * nb;
@@ -117,7 +121,7 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
             const CUtensorMapSwizzle _sw = swizzle_for(L.cin);
             cuuint64_t dims[2] = {(cuuint64_t)L.cin, (cuuint64_t)(planes * 3 * jn * 64)};
             cuuint64_t strides[1] = {(cuuint64_t)L.cin * 2};
-            cuuint32_t box[2] = {(cuuint32_t)L.cin, 64};
+            cuuint32_t box[2] = {(cuuint32_t)L.cin, (cuuint32_t)(P.pair ? 32 : 64)};
             UKBB_ENCODE("group weights", &P.map_b, dt16, 2, (void*)S->wg[li], dims, strides, box, e2);
         }
         {   // output (plain modes): rows of gout pixels x cout channels = 64 elements, box = 16 rows x 8 groups
@@ -150,7 +154,6 @@ static int make_plan(Engine* h, int li, const __nv_bfloat16* in, __nv_bfloat16* 
         cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
         UKBB_ENCODE("activation", &P.map_a, dt16, 4, (void*)in, dims, strides, box, estr);
     }
-    P.pair = (P.kind == 1 && S->f8) ? 1 : 0;        // x2: the 128- / 256-channel halo layers run as CTA pairs, half of the weight rows per CTA
     {   // weights [planes * cout][taps * cin]: the lo plane = rows [cout, 2 cout)
         const int ktot = p.taps * L.cin;
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(planes * L.cout)};
