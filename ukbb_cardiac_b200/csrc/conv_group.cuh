@@ -223,6 +223,9 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    // PAIR: both CTAs' barriers are initialised before any remote arrive / commit, and the collective cta_group::2 allocation has written
+    // the tensor-memory address into BOTH CTAs' slots before either reads it
+    if (PAIR) cluster_sync();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -235,7 +238,6 @@ conv_group_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int walk_step = PAIR ? ((int)gridDim.x >> 1) * 2 : (int)gridDim.x;
     const int n_units = PAIR ? (p.n_tiles + 1) >> 1 : p.n_tiles, unit0 = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x, unit_step = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
     const int my_tiles = unit0 < n_units ? (n_units - unit0 + unit_step - 1) / unit_step : 0;
-    if (PAIR) cluster_sync();                            // both CTAs' barriers are initialised before any remote arrive / commit
 
     if (warp == 0) {
         // ===================== TMA producer =====================

@@ -124,6 +124,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    // both CTAs' barriers are initialised before any remote arrive / multicast; PAIR: the cta_group::2 allocation is collective and writes
+    // the tensor-memory address into BOTH CTAs' slots, so the slot is read after the cluster barrier, not just the CTA barrier
+    if (CL) cluster_sync();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -139,7 +142,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int tile_first = CL ? 2 * ((int)blockIdx.x >> 1) + (int)crank : (int)blockIdx.x;
     const int tile_step = CL ? ((int)gridDim.x >> 1) * 2 : (int)gridDim.x;
     const int tile_end = CL ? ((p.n_tiles + 1) >> 1) * 2 : p.n_tiles;
-    if (CL) cluster_sync();                              // both CTAs' barriers are initialised before any remote arrive / multicast
 
     if (warp == 0) {
         // ===================== TMA producer =====================
