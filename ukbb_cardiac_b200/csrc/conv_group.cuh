@@ -118,18 +118,6 @@ __device__ __forceinline__ uint32_t bn_relu_pack(uint32_t a0, uint32_t a1, float
     else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-// same arithmetic, but the result is split into 16-bit hi and lo pieces (x3 modes): v = max(a * sc + sh, 0) ~ hi + lo
-template <bool F16, bool F8 = false>
-__device__ __forceinline__ void bn_relu_split(uint32_t a0, uint32_t a1, float2 sc, float2 sh, uint32_t& hi, uint32_t& lo) {
-    uint64_t a, b, c, d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(sc.x), "f"(sc.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(sh.x), "f"(sh.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    float x0, x1;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
-    split_pack<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
-}
 // four channels of a 16-channel group (quad q): BN + ReLU, then split_pack4 (tc_common.cuh)
 template <bool F16, bool F8>
 __device__ __forceinline__ void bn_relu_split4(const uint32_t* v, float4 sc, float4 sh, uint32_t* oh, uint32_t* ol, int q) {

@@ -72,7 +72,7 @@ __device__ __forceinline__ uint32_t add_relu_pack(uint32_t a0, uint32_t a1, floa
     return r;
 }
 // same, split into hi and lo 16-bit pieces (x3 modes)
-template <bool F16, bool F8 = false>
+template <bool F16>
 __device__ __forceinline__ void add_relu_split(uint32_t a0, uint32_t a1, float s0, float s1, uint32_t& hi, uint32_t& lo) {
     uint64_t a, sh, d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
@@ -80,7 +80,7 @@ __device__ __forceinline__ void add_relu_split(uint32_t a0, uint32_t a1, float s
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(sh));
     float x0, x1;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
-    split_pack<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
+    split_pack<F16>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
 }
 // four channels (quad q of a 16-channel group): + shift, ReLU, split_pack4 (tc_common.cuh)
 template <bool F16, bool F8>

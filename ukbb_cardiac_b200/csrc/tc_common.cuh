@@ -372,18 +372,9 @@ __device__ __forceinline__ float2 unpack16t(uint32_t u) {
 }
 // split-operand ("x3") modes: a pair of FP32 values -> 16-bit hi pieces and 16-bit lo pieces, v ~ hi + lo with hi = rn16(v) and
 // lo = rn16(v - hi) (v - hi is exact in FP32).  FP16: hi is clamped to the finite range; inputs are >= 0 (post-ReLU) or small.
-// F8 (x2 scheme, FP16 only): `lo` receives [e4m3 pair of (a - hi) * 2^11 | e4m3 pair of hi << 16] (the kernels use split_pack4 below,
-// which writes the group layout [lo8 x 16 | hi8 x 16] directly).
-template <bool F16, bool F8 = false>
+template <bool F16>
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
-    if (F8) {
-        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-        uint16_t l8, h8;
-        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(l8) : "f"((b - h.y) * 2048.f), "f"((a - h.x) * 2048.f));
-        asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(h8) : "f"(h.y), "f"(h.x));
-        lo = (uint32_t)l8 | ((uint32_t)h8 << 16);
-    } else if (F16) {
+    if (F16) {
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
         const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
         uint64_t x, hh;
@@ -431,8 +422,8 @@ __device__ __forceinline__ void split_pack4(float a0, float a1, float a2, float 
         ol[q] = (uint32_t)p01 | ((uint32_t)p23 << 16);
         ol[4 + q] = (uint32_t)q01 | ((uint32_t)q23 << 16);
     } else {
-        split_pack<F16, false>(a0, a1, oh[2 * q], ol[2 * q]);
-        split_pack<F16, false>(a2, a3, oh[2 * q + 1], ol[2 * q + 1]);
+        split_pack<F16>(a0, a1, oh[2 * q], ol[2 * q]);
+        split_pack<F16>(a2, a3, oh[2 * q + 1], ol[2 * q + 1]);
     }
 }
 __device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {

@@ -52,7 +52,7 @@ struct TcState {
     EncodeTiledFn encode = nullptr;
     int fp16 = 0;                            // 16-bit operand format: 0 = BF16, 1 = FP16
     int split = 0;                           // x3 / x2 modes: every operand is a (hi, lo) pair, second plane right after the first
-    int f8 = 0;                              // x2 mode: the lo plane holds FP8 correction operands (tc_common.cuh: split_pack<.., true>)
+    int f8 = 0;                              // x2 mode: the lo plane holds FP8 correction operands (tc_common.cuh: split_pack4<.., true>)
     __nv_bfloat16* w[UKBB_N_CONV] = {};      // [planes][cout][taps*cin], K-major
     __nv_bfloat16* wg[UKBB_N_CONV] = {};     // pixel-group layers: expanded [planes][3 * J tiles][64 rows][cin] (conv_group.cuh)
     __nv_bfloat16* wf[UKBB_N_CONV] = {};     // same_dim0 / fc0 / fc1 with the BN scale folded in before rounding: [planes][cout][cin]
