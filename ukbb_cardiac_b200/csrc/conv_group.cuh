@@ -133,7 +133,7 @@ __device__ __forceinline__ void bn_relu_split4(const uint32_t* v, float4 sc, flo
     float x0, x1, x2, x3;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d0));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x2), "=f"(x3) : "l"(d1));
-    split_pack4<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), fmaxf(x2, 0.f), fmaxf(x3, 0.f), oh, ol, q);
+    split_pack4<F16, F8, true>(x0, x1, x2, x3, oh, ol, q);
 }
 // one 256-bit global store (STG.256): a full 32-byte sector per thread
 __device__ __forceinline__ void stg256(void* p, const uint32_t* v) {

@@ -80,7 +80,7 @@ __device__ __forceinline__ void add_relu_split(uint32_t a0, uint32_t a1, float s
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(sh));
     float x0, x1;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
-    split_pack<F16>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), hi, lo);
+    split_pack_relu<F16>(x0, x1, hi, lo);
 }
 // four channels (quad q of a 16-channel group): + shift, ReLU, split_pack4 (tc_common.cuh)
 template <bool F16, bool F8>
@@ -95,7 +95,7 @@ __device__ __forceinline__ void add_relu_split4(const uint32_t* a, const float* 
     float x0, x1, x2, x3;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d0));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x2), "=f"(x3) : "l"(d1));
-    split_pack4<F16, F8>(fmaxf(x0, 0.f), fmaxf(x1, 0.f), fmaxf(x2, 0.f), fmaxf(x3, 0.f), oh, ol, q);
+    split_pack4<F16, F8, true>(x0, x1, x2, x3, oh, ol, q);
 }
 }  // namespace tc
 

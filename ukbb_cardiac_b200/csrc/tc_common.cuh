@@ -389,13 +389,34 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - __uint_as_float(hi & 0xffff0000u)), "f"(a - __uint_as_float(hi << 16)));
     }
 }
+// max(v, 0) -> (hi, lo) with the ReLU folded into the conversions (FP16): hi = rz16(max(v, 0)) by cvt.rz.relu, so v - hi lies in [0, ulp)
+// for v >= 0 and equals v < 0 otherwise, and lo = cvt.rn.relu(v - hi) is right in both cases -- two FMNMX less per pair than ReLU first,
+// at the price of one bit (hi truncated instead of rounded: 21 instead of 22 significant bits).  BF16: ReLU, then split_pack.
+template <bool F16>
+__device__ __forceinline__ void split_pack_relu(float a, float b, uint32_t& hi, uint32_t& lo) {
+    if (F16) {
+        asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        uint64_t x, hh;
+        float l0, l1;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(hh) : "f"(h.x), "f"(h.y));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(hh));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(l0), "=f"(l1) : "l"(x));
+        asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l1), "f"(l0));
+    } else {
+        split_pack<false>(fmaxf(a, 0.f), fmaxf(b, 0.f), hi, lo);
+    }
+}
 // Four consecutive channels (quad q = 0..3 of a 16-channel group) -> the group's output words: oh[2q], oh[2q + 1] = the 16-bit hi pieces;
 // ol[2q], ol[2q + 1] = the 16-bit lo pieces, or (F8, x2 scheme) ol[q] = four e4m3 bytes of (x - hi) * 2^11 and ol[4 + q] = four e4m3 bytes
 // of hi, i.e. the eight words of a group are [lo8 x 16 | hi8 x 16] with no shuffle afterwards.  hi8 is converted from the packed FP16
 // pair (cvt.e4m3x2.f16x2), the scaling of the lo pieces is one packed multiply per pair.
-template <bool F16, bool F8>
+// RELU: the inputs have NOT been through the ReLU yet (applied here: explicitly for the FP8 layout, folded into the conversions otherwise).
+template <bool F16, bool F8, bool RELU = false>
 __device__ __forceinline__ void split_pack4(float a0, float a1, float a2, float a3, uint32_t* oh, uint32_t* ol, int q) {
     if (F8) {
+        if (RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
         uint32_t h01, h23;
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(a1), "f"(a0));
         asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(a3), "f"(a2));
@@ -422,8 +443,13 @@ __device__ __forceinline__ void split_pack4(float a0, float a1, float a2, float 
         ol[q] = (uint32_t)p01 | ((uint32_t)p23 << 16);
         ol[4 + q] = (uint32_t)q01 | ((uint32_t)q23 << 16);
     } else {
-        split_pack<F16>(a0, a1, oh[2 * q], ol[2 * q]);
-        split_pack<F16>(a2, a3, oh[2 * q + 1], ol[2 * q + 1]);
+        if (RELU) {
+            split_pack_relu<F16>(a0, a1, oh[2 * q], ol[2 * q]);
+            split_pack_relu<F16>(a2, a3, oh[2 * q + 1], ol[2 * q + 1]);
+        } else {
+            split_pack<F16>(a0, a1, oh[2 * q], ol[2 * q]);
+            split_pack<F16>(a2, a3, oh[2 * q + 1], ol[2 * q + 1]);
+        }
     }
 }
 __device__ __forceinline__ float2 unpack16(uint32_t u, int fp16) {
