@@ -204,3 +204,29 @@ def test_member_index_parallel_inflate_and_foreign_files(tmp_path):
     open(p, "wb").write(bytes(bad))
     with pytest.raises(Exception):
         nifti.load(p)
+
+
+def test_x2_plane_format_model():
+    """The FP16 + E4M3 activation planes of the fp16x2 mode as the GPU tests build and decode them (tests/gpu_util.py, a restatement of
+    tc_common.cuh split_pack4): hi = rn_fp16(x), lo plane per 16 channels = [e4m3((x - hi) 2^11) x 16 | e4m3(hi) x 16].  Decoding
+    hi + lo8 2^-11 reproduces x to 2^-15 relative + 2^-21 absolute (a 4-bit correction of a 2^-11 residual), exact zeros stay zero, and the byte layout
+    is the one the kernels read (the lo plane is as large as an FP16 plane)."""
+    import torch
+    from gpu_util import e4m3, x2_decode, x2_planes
+    rng = np.random.default_rng(0)
+    x = np.abs(rng.normal(0.0, 1.0, size=(2, 3, 5, 32))).astype(np.float32)
+    x[0, 0, 0, :4] = 0.0
+    x[1, 2, 4, 5] = 300.0                                         # inside the E4M3 range (448)
+    hi, lo8, hi8, plane = x2_planes(x)
+    assert plane.dtype == np.float16 and plane.shape == x.shape
+    raw = np.ascontiguousarray(plane).view(np.uint8).reshape(x.shape[:-1] + (2, 32))
+    assert (raw[..., :16] == e4m3((x - hi) * 2048.0)[0].reshape(x.shape[:-1] + (2, 16))).all()
+    assert (raw[..., 16:] == e4m3(hi)[0].reshape(x.shape[:-1] + (2, 16))).all()
+    dec = x2_decode(torch.stack([torch.from_numpy(hi).to(torch.float16), torch.from_numpy(plane)]))
+    assert (dec[0, 0, 0, :4] == 0).all()
+    assert np.abs(dec - x).max() <= 2.0 ** -15 * np.abs(x).max()
+    # per element: 2^-4 of a residual <= 2^-11 |x|, or half an E4M3 subnormal step (2^-10) of the scaled residual for small values
+    assert (np.abs(dec - x) <= 2.0 ** -15 * np.abs(x) + 2.0 ** -21).all()
+    # E4M3 codes: round to nearest even, saturating at 448
+    codes, vals = e4m3(np.array([0.0, 1.0, 1.0625, 1.1875, 448.0, 1000.0, -3.0], np.float32))
+    assert vals.tolist() == [0.0, 1.0, 1.0, 1.25, 448.0, 448.0, -3.0]

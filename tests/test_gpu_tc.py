@@ -21,7 +21,7 @@ from ukbb_cardiac_b200 import synth
 from ukbb_cardiac_b200 import weights as W
 from ukbb_cardiac_b200.fcn import FCNEngine
 
-from gpu_util import adjudicate_labels, from_device_labels, from_device_logits, to_device_layout
+from gpu_util import adjudicate_labels, e4m3, from_device_labels, from_device_logits, round16, to_device_layout, x2_decode, x2_planes
 
 pytestmark = pytest.mark.gpu
 
@@ -36,41 +36,11 @@ DICE_FLOOR = {"fp16x3": 0.999, "bf16x3": 0.999, "fp16x2": 0.999, "fp16": 0.99, "
 LOGIT_RTOL = {"fp16x3": 1e-4, "bf16x3": 5e-4, "fp16x2": 2e-4, "fp16": 8e-3, "bf16": 5e-2}
 
 
-def round16(a: np.ndarray, dt) -> np.ndarray:
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dt).to(torch.float32).numpy()
-
-
 def split16(a: np.ndarray, dt):
     """v -> (hi, lo) with hi = rn16(v), lo = rn16(v - hi), as float32 arrays."""
     hi = round16(a, dt)
     lo = round16(np.asarray(a, dtype=np.float32) - hi, dt)
     return hi, lo
-
-
-def e4m3(a: np.ndarray):
-    """float32 -> (uint8 codes, decoded float32) of FP8 E4M3, round to nearest even, saturating at +-448."""
-    q = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
-    return q.view(torch.uint8).numpy(), q.to(torch.float32).numpy()
-
-
-def x2_planes(x32: np.ndarray):
-    """Activation tensor [..., C] -> the two planes of the x2 scheme (tc_common.cuh): hi = rn_fp16(x); lo plane per 16 channels =
-    [e4m3((x - hi) 2^11) x 16 | e4m3(hi) x 16].  Returns (hi, decoded lo8, decoded hi8, lo plane as float16 bit patterns [..., C])."""
-    hi = round16(x32, torch.float16)
-    lo_c, lo_f = e4m3((np.asarray(x32, dtype=np.float32) - hi) * 2048.0)
-    hi_c, hi_f = e4m3(hi)
-    g = x32.shape[:-1] + (x32.shape[-1] // 16, 16)
-    plane = np.concatenate([lo_c.reshape(g), hi_c.reshape(g)], axis=-1)              # [..., C / 16, 32] bytes
-    return hi, lo_f, hi_f, np.ascontiguousarray(plane).view(np.float16).reshape(x32.shape)
-
-
-def x2_decode(o: torch.Tensor) -> np.ndarray:
-    """[2][...][C] float16 tensor written by an x2 kernel -> float64 values hi + lo8 2^-11."""
-    hi = o[0].float().cpu().numpy().astype(np.float64)
-    b = o[1].contiguous().view(torch.uint8).cpu()
-    b = b.reshape(b.shape[:-1] + (b.shape[-1] // 32, 32))[..., :16].contiguous()
-    lo = b.view(torch.float8_e4m3fn).to(torch.float32).numpy().reshape(hi.shape).astype(np.float64)
-    return hi + lo / 2048.0
 
 
 def layer_reference(w, li, x_dev_layout: np.ndarray, dt, split: bool, x2=None) -> np.ndarray:
