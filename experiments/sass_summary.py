@@ -4,12 +4,12 @@ Writes a table to stdout and, with out_dir, the full listing of the kernels on t
 import collections, gzip, re, sys
 path = sys.argv[1]
 out_dir = sys.argv[2] if len(sys.argv) > 2 else None
-KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "FFMA2", "FADD2", "F2FP", "LDG", "STG", "LDS", "STS", "REDG"]
-# kernels on the DEFAULT path (mode fp16x3: F16 = true, SPLIT = true template flags)
-DEFAULT = ["conv_first_tc_kernelILb1ELb1", "conv_group_kernelILi16ELi32ELi2ELb1ELb1", "conv_group_kernelILi32ELi32ELi1ELb1ELb1",
-           "conv_group_kernelILi32ELi64ELi2ELb1ELb1", "conv_group_kernelILi64ELi64ELi1ELb1ELb1", "conv_tc_kernelILi64ELi128ELb1ELb1",
-           "conv_tc_kernelILi64ELi256ELb1ELb1", "conv_halo_kernelILi32ELi128ELb0ELi0ELb1ELb1ELb1", "conv_halo_kernelILi32ELi256ELb0ELi0ELb1ELb1ELb1",
-           "side_tc_kernelILb1ELb1", "head_ts_kernelILi4ELb1ELb1", "int_hist", "int_scan", "lut_kernel", "rescale_lut", "sel_hist0", "sel_histn",
+KEYS = ["UTCHMMA", "UTCQMMA", "2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "FFMA2", "FADD2", "F2FP", "LDG", "STG", "LDS", "STS", "REDG"]
+# kernels on the DEFAULT path (mode fp16x2: F16 = SPLIT = F8 = true template flags; PAIR = true for conv_halo and conv_group 64 -> 64)
+DEFAULT = ["conv_first_tc_kernelILb1ELb1ELb1", "conv_group_kernelILi16ELi32ELi2ELb1ELb1ELb1ELb0", "conv_group_kernelILi32ELi32ELi1ELb1ELb1ELb1ELb0",
+           "conv_group_kernelILi32ELi64ELi2ELb1ELb1ELb1ELb0", "conv_group_kernelILi64ELi64ELi1ELb1ELb1ELb1ELb1", "conv_tc_kernelILi64ELi128ELb1ELb1ELb1",
+           "conv_tc_kernelILi64ELi256ELb1ELb1ELb1", "conv_halo_kernelILi32ELi128ELb0ELi0ELb1ELb1ELb1ELb1ELb1", "conv_halo_kernelILi32ELi256ELb0ELi0ELb1ELb1ELb1ELb1ELb1",
+           "side_tc_kernelILb1ELb1ELb1", "head_ts_kernelILi4ELb1ELb1ELb1", "int_hist", "int_scan", "lut_kernel", "rescale_lut", "sel_hist0", "sel_histn",
            "sel_scan", "sel_final", "sel_init", "rescale_pad", "cc_stats_kernel", "convT_fp32", "lstm_point", "ao_output", "conv_fp32_kernel"]
 cur, funcs = None, collections.OrderedDict()
 for line in open(path, errors="replace"):
@@ -29,7 +29,7 @@ for name, lines in funcs.items():
         n += 1
         op = m.group(1)
         for k in KEYS:
-            if op.startswith(k):
+            if op.startswith(k) or (k == "2CTA" and ".2CTA" in op):
                 ops[k] += 1
     print("%-78s %6d " % (name[:78], n) + " ".join("%7d" % ops[k] for k in KEYS))
 if out_dir:
