@@ -124,6 +124,13 @@ int ukbb_fcn_preprocess(ukbb_fcn* h, float* vol, long long n_slices, int x, int 
                         double q_lo, double q_hi, int x2, int y2, int x_pre, int y_pre,
                         float* out, double* vl_vh, int clip_in_place, void* stream);
 
+/* The second half of ukbb_fcn_preprocess with thresholds the caller already has: out[n][y2][x2] =
+ * float32((double(clip(v, vl, vh)) - vl) / (vh - vl)), zero padding.  For a BLOCK of slices of a sequence whose percentiles were
+ * taken over the whole sequence elsewhere -- one subject split over several GPUs (the slices are independent once
+ * (vl, vh) of common/image_utils.py:70-77 are known; the exchange is 16 bytes, done by the host). */
+int ukbb_fcn_rescale(ukbb_fcn* h, float* vol, long long n_slices, int x, int y, double vl, double vh,
+                     int x2, int y2, int x_pre, int y_pre, float* out, int clip_in_place, void* stream);
+
 /* Whole-subject call on HOST buffers (pinned for full speed): vol [T][Z][Y][X] float32 in,
  * labels [T][Z][Y][X] uint8 out, vl_vh host double[2] out (may be NULL),
  * counts host int64 [n_slices][n_class] out (may be NULL).  Asynchronous on `stream`:

@@ -211,3 +211,15 @@ def test_default_mode_is_the_compliant_one():
     assert deploy.parse_flags(["--mode", "bf16"]).mode == "bf16"
     with pytest.raises(SystemExit):
         deploy.parse_flags(["--mode", "int8"])
+
+
+def test_split_blocks_partition():
+    """SplitEngine's block partition: contiguous, covering, sizes within one of each other, empty blocks allowed."""
+    from ukbb_cardiac_b200.fcn import split_blocks
+    for n in (0, 1, 2, 21, 500, 501):
+        for g in (1, 2, 3, 8):
+            bl = split_blocks(n, g)
+            assert len(bl) == g and bl[0][0] == 0 and bl[-1][1] == n
+            assert all(bl[i][1] == bl[i + 1][0] for i in range(g - 1))
+            sizes = [b - a for a, b in bl]
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)

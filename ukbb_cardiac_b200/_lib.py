@@ -45,6 +45,8 @@ SIGNATURES = {
     "ukbb_fcn_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_double,
                                       C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_void_p]),
+    "ukbb_fcn_rescale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ukbb_fcn_segment_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                         C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ukbb_fcn_class_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

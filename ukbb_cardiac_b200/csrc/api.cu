@@ -293,6 +293,18 @@ int ukbb_fcn_preprocess(ukbb_fcn* hh, float* vol, long long n_slices, int x, int
     return rc;
 }
 
+int ukbb_fcn_rescale(ukbb_fcn* hh, float* vol, long long n_slices, int x, int y, double vl, double vh, int x2, int y2, int x_pre,
+                     int y_pre, float* out, int clip_in_place, void* stream) {
+    Engine* h = reinterpret_cast<Engine*>(hh);
+    UKBB_REQUIRE(h && vol && out, "rescale: null argument");
+    UKBB_CUDA(cudaSetDevice(h->device));
+    UKBB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_ws, 0));       // the selection workspace holds the thresholds
+    const int rc = launch_rescale_given(h->pre, vol, n_slices, x, y, vl, vh, x2, y2, x_pre, y_pre, out, clip_in_place, (cudaStream_t)stream,
+                                        &h->launches);
+    UKBB_CUDA(cudaEventRecord(h->ev_ws, (cudaStream_t)stream));
+    return rc;
+}
+
 int ukbb_fcn_class_counts(ukbb_fcn* hh, long long* counts, int n, void* stream) {
     Engine* h = reinterpret_cast<Engine*>(hh);
     UKBB_REQUIRE(h && counts, "class_counts: null argument");

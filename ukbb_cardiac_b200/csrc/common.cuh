@@ -63,5 +63,7 @@ void preproc_free(PreprocWorkspace& ws);
 int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int x, int y,
                       double q_lo, double q_hi, int x2, int y2, int x_pre, int y_pre, float* out,
                       double* vl_vh_out, int clip_in_place, cudaStream_t st, long long* launches);
+int launch_rescale_given(PreprocWorkspace& ws, float* vol, long long n_slices, int x, int y, double vl, double vh, int x2, int y2,
+                         int x_pre, int y_pre, float* out, int clip_in_place, cudaStream_t st, long long* launches);
 
 }  // namespace ukbb

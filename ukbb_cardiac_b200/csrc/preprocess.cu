@@ -464,4 +464,31 @@ int launch_preprocess(PreprocWorkspace& ws, float* vol, long long n_slices, int 
     return UKBB_OK;
 }
 
+// Rescale + pad with thresholds the caller already has (a block of a sequence whose percentiles were taken over the WHOLE sequence
+// elsewhere: SURVEY 8(e), one subject split over several GPUs).  Same arithmetic as the generic path of launch_preprocess.
+__global__ void set_thresholds_kernel(SelState* st, double* vlvh, double vl, double vh) {
+    vlvh[0] = vl; vlvh[1] = vh;
+    st->done = 0;                     // no lookup table: every voxel goes through the float64 formula
+}
+
+int launch_rescale_given(PreprocWorkspace& ws, float* vol, long long n_slices, int x, int y, double vl, double vh, int x2, int y2,
+                         int x_pre, int y_pre, float* out, int clip_in_place, cudaStream_t st, long long* launches) {
+    UKBB_REQUIRE(n_slices > 0 && x > 0 && y > 0, "rescale: empty volume");
+    UKBB_REQUIRE(x2 % 16 == 0 && y2 % 16 == 0 && x2 >= x + x_pre && y2 >= y + y_pre && x_pre >= 0 && y_pre >= 0,
+                 "rescale: bad padded size %dx%d for %dx%d pre (%d,%d)", x2, y2, x, y, x_pre, y_pre);
+    UKBB_REQUIRE(((uintptr_t)vol & 15) == 0 && ((uintptr_t)out & 15) == 0, "rescale: buffers must be 16-byte aligned");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    SelState* state = reinterpret_cast<SelState*>(ws.state);
+    set_thresholds_kernel<<<1, 1, 0, st>>>(state, ws.vlvh, vl, vh);
+    const long long total4 = n_slices * y2 * (x2 / 4);
+    const long long pad_blocks = (total4 + 255) / 256, pad_cap = (long long)sms * 16;
+    rescale_pad_kernel<<<(unsigned)(pad_blocks < pad_cap ? pad_blocks : pad_cap), 256, 0, st>>>(vol, out, ws.vlvh, total4, x, y, x2, y2,
+                                                                          x_pre, y_pre, clip_in_place, state, ws.lut, 0);
+    if (launches) *launches += 2;
+    UKBB_CUDA(cudaGetLastError());
+    return UKBB_OK;
+}
+
 }  // namespace ukbb

@@ -152,6 +152,21 @@ class FCNEngine:
                 out.data_ptr(), vlvh.data_ptr(), int(clip_in_place), self._stream()))
         return out, vlvh, (x_pre, y_pre)
 
+    def rescale(self, vol: torch.Tensor, n_slices: int, x: int, y: int, vl: float, vh: float,
+                clip_in_place: bool = False, out: Optional[torch.Tensor] = None):
+        """Rescale + pad a block of slices with thresholds (vl, vh) that were taken over the whole sequence elsewhere
+        (`split_blocks` / `SplitEngine`).  vol: cuda float32, n_slices*y*x voxels.  Returns (padded [N, Y2, X2], (x_pre, y_pre))."""
+        assert vol.is_cuda and vol.dtype == torch.float32 and vol.is_contiguous() and vol.numel() == n_slices * x * y
+        x2, x_pre = pad16(x)
+        y2, y_pre = pad16(y)
+        if out is None:
+            out = torch.empty((n_slices, y2, x2), dtype=torch.float32, device=self.device)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n_slices * y2 * x2
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ukbb_fcn_rescale(self._h, vol.data_ptr(), n_slices, x, y, float(vl), float(vh), x2, y2, x_pre, y_pre,
+                                                 out.data_ptr(), int(clip_in_place), self._stream()))
+        return out, (x_pre, y_pre)
+
     # ------------------------------------------------------------------ host-level calls
     def segment_host_async(self, vol: torch.Tensor, shape: Tuple[int, int, int, int], labels: torch.Tensor,
                            vl_vh: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
@@ -382,3 +397,82 @@ class FCNEngine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.ukbb_fcn_launch_count(self._h))
+
+
+def split_blocks(n: int, parts: int):
+    """n slices -> `parts` contiguous blocks [(start, stop), ...], sizes differing by at most one (empty blocks when parts > n)."""
+    base, extra = divmod(n, parts)
+    out, a = [], 0
+    for g in range(parts):
+        b = a + base + (1 if g < extra else 0)
+        out.append((a, b))
+        a = b
+    return out
+
+
+class SplitEngine:
+    """ONE sequence over several GPUs (single-subject latency with G > 1), one process driving all devices.
+
+    The only coupling between the slices of a sequence is the pair of percentile thresholds of rescale_intensity
+    (common/image_utils.py:70-77, taken over the whole 4-D array at deploy_network.py:89).  GPU 0 receives the whole volume, takes
+    the thresholds (and keeps the rescaled slices of its own block); the other GPUs receive only their contiguous block of (z, t)
+    slices while that runs, rescale it with the 16 bytes (vl, vh) the host hands over, and every GPU runs the network on its block.
+    No device collective; labels and class counts are bit-identical to one FCNEngine.segment_volume call."""
+
+    def __init__(self, weights: Dict[str, np.ndarray], devices: Sequence[int], mode: str = DEFAULT_MODE):
+        assert len(devices) >= 1
+        self.devices = [int(d) for d in devices]
+        self.engines = [FCNEngine(weights, device=d, mode=mode) for d in self.devices]
+        self.n_class = self.engines[0].n_class
+
+    def close(self) -> None:
+        for e in self.engines:
+            e.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def segment_volume(self, image: np.ndarray, q: Sequence[float] = (1.0, 99.0)):
+        """image: (X, Y, Z, T), (X, Y, Z) or (X, Y).  Returns what FCNEngine.segment_volume returns."""
+        shp = tuple(image.shape)
+        x, y = shp[0], shp[1]
+        z = shp[2] if image.ndim >= 3 else 1
+        t = shp[3] if image.ndim == 4 else 1
+        n, sl = z * t, x * y
+        host = torch.empty(n * sl, dtype=torch.float32, pin_memory=True)
+        host.numpy()[:] = np.asarray(image, dtype=np.float32).reshape(-1, order="F")
+        blocks = split_blocks(n, len(self.engines))
+        e0 = self.engines[0]
+        # blocks of the other GPUs first (asynchronous copies), then the whole volume to GPU 0
+        dev_blocks = [None] * len(self.engines)
+        for g, (a, b) in enumerate(blocks):
+            if g > 0 and b > a:
+                with torch.cuda.device(self.devices[g]):
+                    dev_blocks[g] = host[a * sl:b * sl].to(self.engines[g].device, non_blocking=True)
+        with torch.cuda.device(self.devices[0]):
+            vol0 = host.to(e0.device, non_blocking=True)
+            padded0, vlvh_dev, (x_pre, y_pre) = e0.preprocess(vol0, n, x, y, q)
+            vlvh = vlvh_dev.cpu()                                    # synchronises GPU 0: the 16 bytes every other GPU needs
+        vl, vh = float(vlvh[0]), float(vlvh[1])
+        labels = torch.empty((n, y, x), dtype=torch.uint8, pin_memory=True)
+        counts = torch.empty((n, self.n_class), dtype=torch.int64, pin_memory=True)
+        for g, (a, b) in enumerate(blocks):
+            if b == a:
+                continue
+            e = self.engines[g]
+            with torch.cuda.device(self.devices[g]):
+                if g == 0:
+                    padded = padded0[a:b]
+                else:
+                    padded, _ = e.rescale(dev_blocks[g], b - a, x, y, vl, vh)
+                lab, _, _ = e.forward(padded, x_pre, y_pre, x, y)
+                labels[a:b].copy_(lab, non_blocking=True)
+                counts[a:b].copy_(e.class_counts(b - a), non_blocking=True)
+        for g, (a, b) in enumerate(blocks):
+            if b > a:
+                torch.cuda.synchronize(self.devices[g])
+        lab = labels.numpy().reshape(-1).reshape(shp, order="F").copy(order="F")      # [n][y][x] is the NIfTI order of the volume
+        return lab, (vl, vh), counts.numpy().reshape(t, z, self.n_class).copy()
