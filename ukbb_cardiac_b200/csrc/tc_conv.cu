@@ -220,10 +220,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 template <int CC, int COUT, bool F16, bool SPLIT, bool F8 = false>
 static int launch_tc2(const TcLayerPlan& P, int sms, cudaStream_t st) {
     using Cfg = ConvTcCfg<CC, COUT, SPLIT, F8>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};          // cudaFuncSetAttribute is per device (one process may drive several: SplitEngine)
+    if (first_use_on_device(attr_set)) {
         UKBB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<CC, COUT, F16, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     const int grid = P.p.n_tiles < sms ? P.p.n_tiles : sms;
     UKBB_CUDA(launch_pdl(conv_tc_kernel<CC, COUT, F16, SPLIT, F8>, grid, 256, Cfg::SMEM_BYTES, st, P.map_a, P.map_b, P.p));
@@ -242,10 +241,9 @@ static int launch_tc_x3(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st
 template <int CC, int COUT, bool F16, bool SPLIT, bool F8 = false, bool PAIR = false>
 static int launch_halo2(const TcLayerPlan& P, int sms, cudaStream_t st) {
     using Cfg = ConvHaloCfg<CC, COUT, false, 0, SPLIT, F8, PAIR>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};          // cudaFuncSetAttribute is per device (one process may drive several: SplitEngine)
+    if (first_use_on_device(attr_set)) {
         UKBB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<CC, COUT, false, 0, F16, true, SPLIT, F8, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     const int pairs = (P.hp.n_tiles + 1) / 2;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
@@ -260,10 +258,9 @@ static int launch_halo(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st)
 template <int CC, int COUT, int STRIDE, bool F16, bool SPLIT, bool F8 = false, bool PAIR = false>
 static int launch_group2(const TcLayerPlan& P, int sms, cudaStream_t st) {
     using Cfg = ConvGroupCfg<CC, COUT, STRIDE, SPLIT, F8, PAIR>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};          // cudaFuncSetAttribute is per device (one process may drive several: SplitEngine)
+    if (first_use_on_device(attr_set)) {
         UKBB_CUDA(cudaFuncSetAttribute(conv_group_kernel<CC, COUT, STRIDE, F16, SPLIT, F8, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     if (PAIR) {                      // clusters of two CTAs, a pair of tiles per cluster and round
         const int pairs = (P.gp.n_tiles + 1) / 2;

@@ -6,10 +6,9 @@ namespace ukbb {
 template <bool F16, bool SPLIT, bool F8 = false>
 static int launch_first2(const TcState* S, const TcLayerPlan& P1, const CUtensorMap& map_img, const ConvFirstParams& fp, int sms, cudaStream_t st) {
     using Cfg = ConvFirstTcCfg<SPLIT, F8>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};          // cudaFuncSetAttribute is per device (one process may drive several: SplitEngine)
+    if (first_use_on_device(attr_set)) {
         UKBB_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<F16, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     const int grid = fp.n_tiles < sms ? fp.n_tiles : sms;
     UKBB_CUDA(launch_pdl(conv_first_tc_kernel<F16, SPLIT, F8>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, st, map_img, P1.map_b, S->map_b0, P1.map_out, fp));

@@ -9,10 +9,9 @@ namespace ukbb {
 template <int NC, bool F16, bool SPLIT, bool F8 = false>
 static int launch_head_ts2(const TcState* S, const HeadParams& hp, int sms, cudaStream_t st) {
     using Cfg = HeadTsCfg<SPLIT>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};          // cudaFuncSetAttribute is per device (one process may drive several: SplitEngine)
+    if (first_use_on_device(attr_set)) {
         UKBB_CUDA(cudaFuncSetAttribute(head_ts_kernel<NC, F16, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr_set = true;
     }
     const int grid = hp.n_tiles < sms ? hp.n_tiles : sms;
     UKBB_CUDA(launch_pdl(head_ts_kernel<NC, F16, SPLIT, F8>, grid, H4_THREADS, Cfg::SMEM, st, S->hm, hp));
@@ -39,10 +38,9 @@ static int launch_head_any(const TcState* S, const HeadParams& hp, int n_class, 
 template <bool F16, bool SPLIT, bool F8 = false>
 static int launch_side2(const TcState* S, const SideParams& sp, int sms, cudaStream_t st) {
     constexpr int SMEM = SPLIT ? SD_SMEM_SPLIT : SD_SMEM;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};          // cudaFuncSetAttribute is per device (one process may drive several: SplitEngine)
+    if (first_use_on_device(attr_set)) {
         UKBB_CUDA(cudaFuncSetAttribute(side_tc_kernel<F16, SPLIT, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
     }
     const int n_tiles = sp.tile_start[4];
     const int grid = n_tiles < sms ? n_tiles : sms;

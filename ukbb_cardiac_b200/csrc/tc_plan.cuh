@@ -95,6 +95,17 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 int launch_plan(const TcLayerPlan& P, int fp16, int sms, cudaStream_t st);
 // tc_first.cu
 int launch_first(const TcState* S, const TcLayerPlan& P1, const CUtensorMap& map_img, const ConvFirstParams& fp, int sms, cudaStream_t st);
+// per-device "done once" flags of the launchers (function attributes belong to a device)
+constexpr int kMaxDevices = 64;
+inline bool first_use_on_device(bool (&seen)[kMaxDevices]) {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= kMaxDevices - 1;
+    if (seen[d]) return false;
+    seen[d] = true;
+    return true;
+}
+
 // tc_head.cu (16-bit operands) / tc_head_x3.cu (split operands)
 int launch_side_16(const TcState* S, const SideParams& sp, int sms, cudaStream_t st);
 int launch_head_16(const TcState* S, const HeadParams& hp, int n_class, int sms, cudaStream_t st);
